@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark: grid points/sec of the fused MLP + finite-difference physics loss at 256^3.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--hidden H] [--grid n] [--impl reference]
+
+One "step" = one pass of the hot path over the whole synthetic grid: three MLP evaluations per
+point (t-dt, t, t+dt), the PDE residuals and the reduction to {L_sigma, L_u}.  Synthetic inputs as
+the reference's test/test_mlp_phys_perf.cpp:21-23: GridSpec{n,n,n, h=1, dt=2e-3, periodic},
+MinusOneToOne coordinates, mlp_random_init(seed 777, scale 0.25), t = 0.25, weights (1,1).
+There are no input arrays: coordinates derive from the point index and the weights (2.3 KB at H=64)
+ride in the kernel-parameter constant bank, so nothing needs to be (or can be) warm in L2; the L2
+is flushed between timed steps anyway.  With N > 1 the grid is sharded into z-slabs (one per rank,
+halo planes recomputed) and one NCCL all-reduce of two doubles combines the partial sums: total
+work is fixed, i.e. strong scaling.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "grid points/sec, fused MLP + finite-difference physics loss"
+UNIT = "points/s"
+T0, DT, SEED, SCALE = 0.25, 2e-3, 777, 0.25
+
+
+def flops_per_point(H: int) -> int:
+    """Algorithmic work, SURVEY.md section 8(d): 3 slices x 2*(4H + 4H) MLP flops + 3H ReLU + 60 stencil + 8 reduction."""
+    return 51 * H + 68
+
+
+def strict_fp32_peak():
+    """Measured FMUL+FADD (non-contracted) pipe peak of this pool's B200, TFLOP/s, and where it came from."""
+    p = os.path.join(ROOT, "profiles", "r01_microbench_fp32_long.json")
+    try:
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["strict"]["tflops"]), float(d["ffma"]["tflops"]), "measured: tools/microbench_fp32.cu -> " + os.path.relpath(p, ROOT)
+    except Exception:
+        return 37.2, 74.4, "fallback: 148 SM x 128 lanes x 1.965 GHz (SURVEY.md section 8d)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] if pw else sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(H: int, nxy: int, planes: int, threads: int):
+    """Reference CPU path (oracle/_ref: the unmodified reference sources; else the pinned C port) on an
+    nxy x nxy x planes grid with the benchmark's weights/t/dt.  Returns (points/s, kind, cores, losses)."""
+    import oracle
+    from oracle import Grid
+    R = oracle.reference()
+    g = Grid(nxy, nxy, planes, 1.0, 1.0, 1.0, DT, True)
+    if R is not None:
+        w = R.mlp_random_init(H, SEED, SCALE)
+        t0 = time.perf_counter()
+        r = R.fused_loss(g, w, T0, DT, threads=threads)
+        dt = time.perf_counter() - t0
+        return g.N / dt, "reference", threads, (float(r["loss_sigma"]), float(r["loss_u"]))
+    P = oracle.port()
+    w = P.mlp_random_init(H, SEED, SCALE)
+    t0 = time.perf_counter()
+    r = P.fused_loss(g, w, T0, DT)
+    dt = time.perf_counter() - t0
+    return g.N / dt, "port", 1, (float(r["loss_sigma"]), float(r["loss_u"]))
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    H, n = args.hidden, args.grid
+    threads = host_threads()
+    planes = max(3, min(n, args.ref_planes))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_rate(H, n, planes, threads)
+    times, kind, cores = [], "port", 1
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        rate, kind, cores, _ = cpu_reference_rate(H, n, planes, threads)
+        times.append(time.perf_counter() - t0)
+    pts = n * n * planes
+    total = sum(times)
+    value = pts * len(times) / total
+    sample = f"{n}x{n}x{planes} planes of the {n}^3 workload per step (same weights, t, dt, periodic), {cores} host threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"fused MLP(4-{H}-4)+phys loss, {n}^3 grid, seed {SEED}, dt {DT}, periodic", "hidden": H,
+                   "grid": [n, n, n], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--hidden", type=int, default=64)
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", type=int, default=-1, help="fused-kernel launch variant (tuning)")
+    ap.add_argument("--ref-planes", type=int, default=32, help="z planes per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="also time H=32 and H=128 (reported under 'extra')")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from phys_autodiff_b200 import Grid, MLPConfig, PhysWeights, ops
+    from phys_autodiff_b200.ops import slab_for_rank
+
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+
+    H, n = args.hidden, args.grid
+    g = Grid(n, n, n, 1.0, 1.0, 1.0, DT, True)
+    cfg = MLPConfig(4, H, 4, True)
+    pw = PhysWeights(1.0, 1.0)
+    w = ops.mlp_random_init(H, SEED, SCALE)
+    ctx = ops.Context(local)
+    if args.variant >= 0:
+        ctx.set_fused_variant(args.variant)
+    ctx.set_weights(cfg, *w)
+    slab = slab_for_rank(n, rank, world)
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        ctx.fused_loss_acc(g, T0, DT, slab=slab, acc=acc)
+        if world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+
+    def timed(K, W, sampler=None):
+        for _ in range(W):
+            step()
+        barrier()
+        if sampler:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        l0 = ctx.launch_count
+        wall0 = time.perf_counter()
+        for e0, e1 in ev:
+            flush.zero_()          # L2 flush between timed steps (outside the per-step events)
+            e0.record()
+            step()
+            e1.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler else None
+        per = [e0.elapsed_time(e1) for e0, e1 in ev]
+        tot = torch.tensor([sum(per)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return tot.item(), per, ctx.launch_count - l0, clocks, wall
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    total_ms, per, launches, clocks, wall = timed(args.steps, max(3, args.warmup), sampler)
+    value = g.N * args.steps / (total_ms * 1e-3)
+    ls, lu = ctx.finalize(acc.cpu().numpy(), pw, g.N)
+
+    # kernel-only duration on this rank (no all-reduce inside the events) for the roofline
+    def kernel_only(K):
+        for _ in range(3):
+            ctx.fused_loss_acc(g, T0, DT, slab=slab, acc=acc)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(K):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ctx.fused_loss_acc(g, T0, DT, slab=slab, acc=acc); e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.mean(ts), min(ts)
+    k_mean, k_min = kernel_only(min(args.steps, 20))
+    slab_pts = (slab[1] - slab[0]) * n * n
+    peak_strict, peak_ffma, peak_src = strict_fp32_peak()
+    achieved = flops_per_point(H) * slab_pts / (k_mean * 1e-3) / 1e12
+
+    # end to end through the public API with host buffers: weights H2D + kernel (+ all-reduce) + D2H of the sums
+    def e2e(K):
+        for _ in range(3):
+            ctx.set_weights(cfg, *w); ctx.fused_loss(g, pw, T0, DT)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            ctx.set_weights(cfg, *w)
+            out = ctx.fused_loss(g, pw, T0, DT)
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return g.N * K / t.item(), out
+    e2e_value, e2e_out = e2e(args.steps)
+    h2d = sum(int(a.nbytes) for a in w)
+
+    extra = {}
+    if args.extra and world == 1:
+        for H2 in (32, 128):
+            w2 = ops.mlp_random_init(H2, SEED, SCALE)
+            ctx.set_weights(MLPConfig(4, H2, 4, True), *w2)
+            t_ms, _, _, _, _ = timed(10, 3)
+            extra[f"H{H2}"] = {"value": g.N * 10 / (t_ms * 1e-3), "unit": UNIT,
+                               "tflops_algorithmic": flops_per_point(H2) * g.N * 10 / (t_ms * 1e-3) / 1e12}
+        ctx.set_weights(cfg, *w)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        planes = 64 if threads >= 8 else 16
+        rate, kind, cores, closs = cpu_reference_rate(H, n, planes, threads)
+        rate1, _, _, _ = cpu_reference_rate(H, n, 4, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{n}x{n}x{planes} planes of the workload grid on {cores} host threads "
+                         f"(reference is single-threaded: 1 thread on {n}x{n}x4 = {rate1:.4g} points/s)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fused MLP(4-{H}-4)+phys loss, {n}^3 grid, seed {SEED}, scale {SCALE}, t {T0}, dt {DT}, "
+                                   f"h 1, periodic, MinusOneToOne (test_mlp_phys_perf.cpp:21-23 at 256^3)",
+                       "hidden": H, "grid": [n, n, n], "parallelism": f"z-slab x{world}, halo recomputed, 1 all-reduce of 2 doubles",
+                       "mode": "strict fp32 (FMUL+FADD, bit-exact MLP)",
+                       "l2": "no HBM-resident inputs (coordinates from index, weights in the constant bank); L2 flushed "
+                             "between timed steps with a 256 MiB write outside the per-step events",
+                       "fused_variant": args.variant},
+            "loss": {"sigma": float(ls), "u": float(lu)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                    "loss": [float(e2e_out[0]), float(e2e_out[1])]},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32-pipe", "achieved": achieved, "peak": peak_strict, "unit": "TFLOP/s",
+                         "frac": achieved / peak_strict, "traffic": None,
+                         "peak_source": peak_src, "peak_ffma": peak_ffma,
+                         "flops_per_point": flops_per_point(H), "kernel_ms_mean": k_mean, "kernel_ms_min": k_min,
+                         "note": "algorithmic flops (51H+68)/point x slab points / CUDA-event kernel time; peak = measured "
+                                 "non-contracted FMUL+FADD rate (parity mode cannot use FFMA); HBM traffic is ~0 by design"},
+            "cpu_baseline": cpu,
+            "wall_s_timed_region": wall,
+        }
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,29 @@
+// Additive C++ entry points of the B200 build, in the style of include/phys.h / mlp_grid.h: the
+// operations the reference planned but never shipped.  Host-pointer,
+// void-returning, abort-with-message on CUDA errors, like the wrappers of the existing names.
+#ifndef PHYS_AUTODIFF_PHYS_B200_H
+#define PHYS_AUTODIFF_PHYS_B200_H
+
+#include "mlp_grid.h"
+#include "phys.h"
+
+namespace phys {
+
+// Loss forward on the single-kernel stencil with on-device reduction -- the
+// cuda_phys_loss_forward_fused named in the reference's docs/PLAN_FUSED_PHYS_LOSS.md:59.
+void cuda_phys_loss_forward_fused(const GridSpec& g, const PhysWeights& w, const float* sigma_tm1, const float* sigma_t,
+                                  const float* sigma_tp1, const float* u_tm1, const float* u_t, const float* u_tp1,
+                                  float* out_loss_sigma, float* out_loss_u, float* opt_R_sigma = nullptr,
+                                  float* opt_R_ux = nullptr, float* opt_R_uy = nullptr, float* opt_R_uz = nullptr);
+
+// The whole hot path in one kernel: MLP at (x,y,z,t-dt|t|t+dt) over the grid -> residuals -> loss.
+// Equivalent to mlp_generate_fields_cuda followed by cuda_phys_loss_forward_*, without any field
+// ever leaving the chip (the "MLP -> physics mega-kernel" of docs/BENCHMARK_REPORT.md:61).
+// Requires cfg.dims.In == cfg.dims.Out == 4 and H <= 128.
+void mlp_phys_loss_fused_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, const PhysWeights& pw,
+                              float t, float dt, float* out_loss_sigma, float* out_loss_u, float* opt_R_sigma = nullptr,
+                              float* opt_R_ux = nullptr, float* opt_R_uy = nullptr, float* opt_R_uz = nullptr);
+
+}  // namespace phys
+
+#endif  // PHYS_AUTODIFF_PHYS_B200_H

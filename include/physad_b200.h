@@ -1,0 +1,186 @@
+/*
+ * physad_b200.h -- C-ABI of the B200-native (sm_100a) phys-autodiff hot path.
+ *
+ * This is the drop-in boundary: plain C, POD structs, raw pointers and sizes, an int status on
+ * every call (0 = ok; otherwise a cudaError_t value or PHYSAD_E_*), no torch / C++ types.  The
+ * reference's C++ API (include/backend.h, mlp.h, mlp_grid.h, phys.h -- host-pointer, void-returning
+ * free functions) is implemented in phys_autodiff_b200/csrc/cxx_api.cpp as thin wrappers over the
+ * functions below; INTEGRATION.md shows the binding.  Each entry point cites the reference
+ * interface it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   *_dev  : every data pointer is a DEVICE pointer on the current device; `stream` is a
+ *            cudaStream_t passed as void* (NULL = legacy default stream); the call only enqueues.
+ *   *_host : every data pointer is a HOST pointer (pageable is fine, as in the reference, whose
+ *            API is host-pointer only -- include/phys.h:66); the call stages through device
+ *            scratch owned by the context, runs the same kernels and blocks until results are
+ *            back in the caller's buffers.
+ *   Layouts follow the reference: linear index (z*ny + y)*nx + x, x fastest (src/phys_cpu.cpp:17-19);
+ *   vector fields are channel-major [ux(0..N-1), uy, uz] (include/phys.h:20-21); MLP outputs are
+ *   AoS [sigma,ux,uy,uz] per point (include/mlp_grid.h:16).
+ *   There is no CPU fallback anywhere behind this header: without a CUDA device every compute
+ *   entry point returns an error.
+ */
+#ifndef PHYSAD_B200_H
+#define PHYSAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHYSAD_ABI_VERSION 1
+
+enum {
+    PHYSAD_OK = 0,
+    PHYSAD_E_INVALID = -1,     /* bad argument (null pointer, non-positive size, ...) */
+    PHYSAD_E_UNSUPPORTED = -2, /* shape outside what the kernels are built for */
+    PHYSAD_E_NOWEIGHTS = -3    /* context has no weights yet */
+};
+
+/* phys::GridSpec, include/phys.h:8-13 (bool widened to int for C). */
+typedef struct physad_grid {
+    int nx, ny, nz;
+    float hx, hy, hz;
+    float dt;
+    int periodic;
+} physad_grid;
+
+/* phys::PhysWeights, include/phys.h:15-18. */
+typedef struct physad_phys_weights {
+    float w_sigma, w_u;
+} physad_phys_weights;
+
+/* phys::MLPDims + phys::CoordNorm, include/mlp_grid.h:13-17,26.  norm: 0 = ZeroToOne, 1 = MinusOneToOne. */
+typedef struct physad_mlp_config {
+    int In, H, Out;
+    int norm;
+} physad_mlp_config;
+
+/* z-slab of the global grid owned by one rank: planes [z_begin, z_end).  Coordinates, wrap and
+ * clamp always refer to the GLOBAL grid; halo planes are recomputed, never exchanged. */
+typedef struct physad_slab {
+    int z_begin, z_end;
+} physad_slab;
+
+typedef struct physad_ctx physad_ctx; /* opaque: resident weights, reduction scratch, staging */
+
+int physad_abi_version(void);
+/* Message for the last non-zero status returned on this thread ("" if none). */
+const char* physad_last_error(void);
+const char* physad_error_string(int status);
+
+/* ---- context --------------------------------------------------------------------------- */
+/* Binds to CUDA device `device` (-1 = current).  Fails if no sm_100 device is present. */
+int physad_ctx_create(physad_ctx** out, int device);
+int physad_ctx_destroy(physad_ctx* ctx);
+/* Number of SMs of the bound device (grid sizing is derived from it). */
+int physad_ctx_sm_count(const physad_ctx* ctx);
+
+/* Make weights resident.  HOST pointers, layouts of phys::MLPWeights (include/mlp_grid.h:19-24):
+ * W1[H*In] row-major, b1[H], W2[Out*H] row-major, b2[Out].  Replaces the per-call upload in
+ * mlp_forward<ExecCuda> (src/mlp_cuda.cu:102-106).  Cheap (a few KB); call again after an update. */
+int physad_set_weights(physad_ctx* ctx, const physad_mlp_config* cfg, const float* W1, const float* b1,
+                       const float* W2, const float* b2);
+
+/* ---- MLP operator ---------------------------------------------------------------------- */
+/* y[B*Out] = MLP(x[B*In]) with the context's weights; any In/H/Out that fits shared memory.
+ * Replaces mlp_forward<ExecCuda> (include/mlp.h:5-6, src/mlp_cuda.cu:91-121) / mlp_infer_cuda
+ * (include/mlp_grid.h:41).  Bit-exact with mlp_forward<ExecCpu> (src/mlp_cpu.cpp:14-36). */
+int physad_mlp_forward_dev(physad_ctx* ctx, const float* x, float* y, size_t B, void* stream);
+int physad_mlp_forward_host(physad_ctx* ctx, const float* x, float* y, size_t B);
+
+/* MLP over the grid at time t, coordinates generated from the point index (never materialised).
+ * out: AoS [slab points][4].  Replaces mlp_grid_infer_cuda (include/mlp_grid.h:45,
+ * src/mlp_grid.cpp:61-67).  Requires In = Out = 4. */
+int physad_mlp_grid_infer_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float* out,
+                              void* stream);
+int physad_mlp_grid_infer_host(physad_ctx* ctx, const physad_grid* g, float t, float* out);
+
+/* Six physics input fields at t-dt, t, t+dt in one pass (sigma_*: n, u_*: 3n channel-major, n =
+ * slab points).  Replaces mlp_generate_fields_cuda (include/mlp_grid.h:55-57, src/mlp_grid.cpp:95-106). */
+int physad_mlp_generate_fields_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float dt,
+                                   float* sigma_tm1, float* sigma_t, float* sigma_tp1, float* u_tm1, float* u_t,
+                                   float* u_tp1, void* stream);
+int physad_mlp_generate_fields_host(physad_ctx* ctx, const physad_grid* g, float t, float dt, float* sigma_tm1,
+                                    float* sigma_t, float* sigma_tp1, float* u_tm1, float* u_t, float* u_tp1);
+
+/* ---- physics operators on supplied fields (whole grid, single device) -------------------- */
+/* Residuals.  Replaces cuda_phys_residuals_fused / _nonfused (include/phys.h:67-77,120-130).
+ * kernel_ms (host pointer, may be NULL) receives the kernel-only time of the _host variant, as the
+ * reference's *_timed wrappers report (include/phys.h:106-117,145-156). */
+int physad_phys_residuals_dev(physad_ctx* ctx, const physad_grid* g, const float* sigma_tm1, const float* sigma_t,
+                              const float* sigma_tp1, const float* u_tm1, const float* u_t, const float* u_tp1,
+                              float* R_sigma, float* R_ux, float* R_uy, float* R_uz, void* stream);
+int physad_phys_residuals_host(physad_ctx* ctx, const physad_grid* g, const float* sigma_tm1, const float* sigma_t,
+                               const float* sigma_tp1, const float* u_tm1, const float* u_t, const float* u_tp1,
+                               float* R_sigma, float* R_ux, float* R_uy, float* R_uz, float* kernel_ms);
+
+/* Loss forward with the reduction ON THE DEVICE (the reference sums on the host,
+ * src/phys_cuda_nonfused.cu:385-393).  acc_dev[2] (device, double) receives {sum R_sigma^2,
+ * sum |R_u|^2}; R_* may be NULL.  Replaces cuda_phys_loss_forward_nonfused (include/phys.h:79-92)
+ * and supplies the cuda_phys_loss_forward_fused the reference only planned
+ * (docs/PLAN_FUSED_PHYS_LOSS.md:59). */
+int physad_phys_loss_dev(physad_ctx* ctx, const physad_grid* g, const float* sigma_tm1, const float* sigma_t,
+                         const float* sigma_tp1, const float* u_tm1, const float* u_t, const float* u_tp1,
+                         double* acc_dev, float* R_sigma, float* R_ux, float* R_uy, float* R_uz, void* stream);
+int physad_phys_loss_host(physad_ctx* ctx, const physad_grid* g, const physad_phys_weights* w, const float* sigma_tm1,
+                          const float* sigma_t, const float* sigma_tp1, const float* u_tm1, const float* u_t,
+                          const float* u_tp1, float* loss_sigma, float* loss_u, float* R_sigma, float* R_ux,
+                          float* R_uy, float* R_uz);
+
+/* Residual VJP g = (2 w / float(N)) R.  Replaces cuda_phys_loss_backward_nonfused
+ * (include/phys.h:94-103; CPU: src/phys_cpu.cpp:151-170). */
+int physad_phys_backward_dev(physad_ctx* ctx, const physad_grid* g, const physad_phys_weights* w, const float* R_sigma,
+                             const float* R_ux, const float* R_uy, const float* R_uz, float* g_sigma, float* g_ux,
+                             float* g_uy, float* g_uz, void* stream);
+int physad_phys_backward_host(physad_ctx* ctx, const physad_grid* g, const physad_phys_weights* w, const float* R_sigma,
+                              const float* R_ux, const float* R_uy, const float* R_uz, float* g_sigma, float* g_ux,
+                              float* g_uy, float* g_uz);
+/* Same VJP recomputed from the fields.  Replaces cuda_phys_loss_backward_fused (include/phys.h:132-143). */
+int physad_phys_backward_from_fields_dev(physad_ctx* ctx, const physad_grid* g, const physad_phys_weights* w,
+                                         const float* sigma_tm1, const float* sigma_t, const float* sigma_tp1,
+                                         const float* u_tm1, const float* u_t, const float* u_tp1, float* g_sigma,
+                                         float* g_ux, float* g_uy, float* g_uz, void* stream);
+int physad_phys_backward_from_fields_host(physad_ctx* ctx, const physad_grid* g, const physad_phys_weights* w,
+                                          const float* sigma_tm1, const float* sigma_t, const float* sigma_tp1,
+                                          const float* u_tm1, const float* u_t, const float* u_tp1, float* g_sigma,
+                                          float* g_ux, float* g_uy, float* g_uz);
+
+/* ---- the metric path: fused MLP + finite-difference residual + loss reduction ------------ */
+/* One kernel: evaluates the MLP at (x,y,z,t-dt|t|t+dt) for every point of the slab (plus the
+ * recomputed stencil halo), forms the residuals of src/phys_cpu.cpp:25-110 and reduces
+ * {sum R_sigma^2, sum |R_u|^2} over the slab into acc_dev[2] (device, double).  No field ever
+ * touches HBM.  R_* (device, slab-local, may be NULL) receive the residuals.  This composes
+ * mlp_generate_fields_cuda + cuda_phys_loss_forward_* of the reference (call stack B/C of
+ * SURVEY.md section 3); the reference has no such entry point (docs/BENCHMARK_REPORT.md:61).
+ * Requires In = Out = 4.  After a multi-rank sum of acc_dev, physad_finalize_loss gives the loss. */
+int physad_fused_loss_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float dt,
+                          double* acc_dev, float* R_sigma, float* R_ux, float* R_uy, float* R_uz, void* stream);
+/* Host-buffer form: uploads the given weights, runs the kernel on the whole grid, returns the two
+ * losses (and residuals if the pointers are non-NULL).  This is the call `e2e` in bench.py times. */
+int physad_fused_loss_host(physad_ctx* ctx, const physad_grid* g, const physad_mlp_config* cfg, const float* W1,
+                           const float* b1, const float* W2, const float* b2, const physad_phys_weights* w, float t,
+                           float dt, float* loss_sigma, float* loss_u, float* R_sigma, float* R_ux, float* R_uy,
+                           float* R_uz);
+/* L = float(w * acc * (1.0 / N_global)) exactly as src/phys_cpu.cpp:146-148.  Pure host arithmetic. */
+void physad_finalize_loss(const double acc[2], const physad_phys_weights* w, size_t n_global, float* loss_sigma,
+                          float* loss_u);
+
+/* Weight initialiser of the grid driver for non-C++ hosts: uniform [-scale, scale] from
+ * std::mt19937(seed) in the order W1, b1, W2, b2.  Replaces phys::mlp_random_init
+ * (include/mlp_grid.h:34, src/mlp_grid.cpp:8-19).  HOST pointers; no device work. */
+void physad_mlp_random_init(int In, int H, int Out, unsigned int seed, float scale, float* W1, float* b1, float* W2,
+                            float* b2);
+
+/* Tuning knob for experiments: selects the fused-kernel variant (0 = default). Returns the previous value. */
+int physad_set_fused_variant(physad_ctx* ctx, int variant);
+/* Number of kernel launches this context has enqueued since creation (bench.py's gpu_launches). */
+uint64_t physad_launch_count(const physad_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYSAD_B200_H */

@@ -1,0 +1,712 @@
+// C-ABI implementation (include/physad_b200.h): context, resident weights, launch geometry and
+// the host-pointer staging wrappers.  All arithmetic lives in the kernels (*.cuh); this file only
+// decides shapes, fills the kernel-parameter weight block and moves bytes.
+#include "../../include/physad_b200.h"
+#include "stage_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace physad;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(int(e_), std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+}  // namespace
+
+struct physad_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;  // used by the *_host entry points
+    physad_mlp_config cfg{4, 0, 4, 1};
+    bool has_weights = false;
+    std::vector<float> W1, b1, W2, b2;                             // host copy (feeds the parameter block)
+    float *dW1 = nullptr, *db1 = nullptr, *dW2 = nullptr, *db2 = nullptr;  // device copy (generic MLP kernels)
+    size_t dW_cap[4] = {0, 0, 0, 0};
+    double2* partials = nullptr;
+    size_t partials_cap = 0;
+    unsigned int* ticket = nullptr;
+    double* d_acc = nullptr;  // [2]
+    double* h_acc = nullptr;  // pinned [2]
+    char* scratch = nullptr;  // device staging for *_host calls
+    size_t scratch_cap = 0;
+    uint64_t launches = 0;
+    int fused_variant = 0;
+};
+
+namespace {
+
+int ensure_partials(physad_ctx* c, size_t blocks) {
+    if (blocks <= c->partials_cap) return 0;
+    if (c->partials) CU(cudaFree(c->partials));
+    c->partials = nullptr;
+    c->partials_cap = 0;
+    CU(cudaMalloc(&c->partials, blocks * sizeof(double2)));
+    c->partials_cap = blocks;
+    return 0;
+}
+
+int ensure_scratch(physad_ctx* c, size_t bytes) {
+    if (bytes <= c->scratch_cap) return 0;
+    if (c->scratch) CU(cudaFree(c->scratch));
+    c->scratch = nullptr;
+    c->scratch_cap = 0;
+    CU(cudaMalloc(&c->scratch, bytes));
+    c->scratch_cap = bytes;
+    return 0;
+}
+
+int check_grid(const physad_grid* g) {
+    if (!g) return fail(PHYSAD_E_INVALID, "grid is null");
+    if (g->nx <= 0 || g->ny <= 0 || g->nz <= 0) return fail(PHYSAD_E_INVALID, "grid extents must be positive");
+    if (size_t(g->nx) * g->ny * g->nz >= (size_t(1) << 31))
+        return fail(PHYSAD_E_UNSUPPORTED, "N >= 2^31 (the reference indexes with int, src/phys_cuda_fused.cu:187)");
+    return 0;
+}
+
+int check_slab(const physad_grid* g, const physad_slab* s, physad_slab* out) {
+    physad_slab r{0, g->nz};
+    if (s) r = *s;
+    if (r.z_begin < 0 || r.z_end > g->nz || r.z_begin > r.z_end) return fail(PHYSAD_E_INVALID, "slab outside the grid");
+    *out = r;
+    return 0;
+}
+
+// float(1 / (2 h)) with the quotient formed in double as the CPU reference does (src/phys_cpu.cpp:38-41)
+float inv2(float h) { return float(1.0 / (2.0 * double(h))); }
+
+int template_h(int H) { return H <= 32 ? 32 : (H <= 64 ? 64 : (H <= 128 ? 128 : 0)); }
+
+// Fill the kernel-parameter weight block.  Hidden units beyond cfg.H are zero records: they
+// contribute act = relu(0) = 0 and products 0, which leave every accumulator unchanged.
+template <int H>
+void fill_const(const physad_ctx* c, const float tcoord[3], MlpConst<H>& k) {
+    const int h_rt = c->cfg.H;
+    for (int h = 0; h < H; ++h) {
+        if (h < h_rt) {
+            const float* w = &c->W1[size_t(h) * 4];
+            k.l1[h] = make_float4(c->b1[h], w[0], w[1], w[2]);
+            // separately rounded fp32 products W1[h,3]*t (volatile keeps the compiler from folding
+            // them into anything wider)
+            volatile float pm = w[3] * tcoord[0], p0 = w[3] * tcoord[1], pp = w[3] * tcoord[2];
+            k.lt[h] = make_float4(pm, p0, pp, 0.f);
+            k.w2[h] = make_float4(c->W2[h], c->W2[size_t(h_rt) + h], c->W2[2 * size_t(h_rt) + h], c->W2[3 * size_t(h_rt) + h]);
+        } else {
+            k.l1[h] = k.lt[h] = k.w2[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    k.b2 = make_float4(c->b2[0], c->b2[1], c->b2[2], c->b2[3]);
+}
+
+// 4th MLP input for a time value (reference src/mlp_grid.cpp:38)
+float time_coord(float t, int norm) { return norm == 1 ? t : (t + 0.5f); }
+
+int need_4x4(const physad_ctx* c, const char* what) {
+    if (!c->has_weights) return fail(PHYSAD_E_NOWEIGHTS, std::string(what) + ": no weights set");
+    if (c->cfg.In != 4 || c->cfg.Out != 4)
+        return fail(PHYSAD_E_UNSUPPORTED, std::string(what) + ": grid paths need In = Out = 4 (src/mlp_grid.cpp:69-80)");
+    if (template_h(c->cfg.H) == 0) return fail(PHYSAD_E_UNSUPPORTED, std::string(what) + ": H > 128 not built");
+    return 0;
+}
+
+// ---- fused kernel launch -----------------------------------------------------------------
+struct FusedGeom {
+    int tiles_x, tiles_y, nchunks;
+    size_t smem;
+};
+
+template <int H, int P, int TYB, int UNROLL, int MINB>
+int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], float dt, double* acc,
+                   float* const R[4], cudaStream_t st) {
+    constexpr int TX = 32, TY = TYB * P;
+    auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB>;
+    const size_t smem = size_t(4) * 4 * (TX + 2) * (TY + 2) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr_done = true;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * TYB, smem));
+    if (per_sm < 1) return fail(PHYSAD_E_UNSUPPORTED, "fused kernel does not fit on an SM");
+    const int tiles_x = (g->nx + TX - 1) / TX, tiles_y = (g->ny + TY - 1) / TY;
+    const int tiles = tiles_x * tiles_y, nzl = s.z_end - s.z_begin;
+    const long long slots = (long long)per_sm * c->sm_count;
+    // z chunks: minimise waves * (planes per chunk + cost of the two time-t-only halo planes)
+    int best_nc = 1;
+    if (const char* e = getenv("PHYSAD_NCHUNKS")) {
+        best_nc = std::max(1, std::min(nzl, atoi(e)));
+    } else {
+        double best = 1e300;
+        for (int nc = 1; nc <= nzl; ++nc) {
+            const long long blocks = (long long)tiles * nc;
+            const double waves = double((blocks + slots - 1) / slots);
+            const double cost = waves * (double((nzl + nc - 1) / nc) + 0.75);
+            if (cost < best * 0.999) { best = cost; best_nc = nc; }
+        }
+    }
+    FusedArgs a{};
+    a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
+    a.z_begin = s.z_begin; a.z_end = s.z_end;
+    a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.nchunks = best_nc;
+    a.m1p1 = c->cfg.norm == 1; a.periodic = g->periodic != 0;
+    a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
+    const size_t blocks = size_t(tiles) * best_nc;
+    if (int rc = ensure_partials(c, blocks)) return rc;
+    a.partials = c->partials; a.ticket = c->ticket; a.acc_out = acc;
+    for (int k = 0; k < 4; ++k) a.R[k] = R[k];
+    MlpConst<H> k;
+    fill_const<H>(c, tc, k);
+    (void)dt;
+    kern<<<unsigned(blocks), 32 * TYB, smem, st>>>(k, a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int H>
+int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], float dt, double* acc,
+                   float* const R[4], cudaStream_t st) {
+    switch (c->fused_variant) {
+        default:
+        case 0: return launch_fused_t<H, 2, 8, 4, 2>(c, g, s, tc, dt, acc, R, st);
+        case 1: return launch_fused_t<H, 1, 16, 4, 2>(c, g, s, tc, dt, acc, R, st);
+        case 2: return launch_fused_t<H, 2, 16, 4, 1>(c, g, s, tc, dt, acc, R, st);
+        case 3: return launch_fused_t<H, 4, 8, 2, 1>(c, g, s, tc, dt, acc, R, st);
+        case 4: return launch_fused_t<H, 2, 8, 8, 2>(c, g, s, tc, dt, acc, R, st);
+        case 5: return launch_fused_t<H, 1, 8, 4, 4>(c, g, s, tc, dt, acc, R, st);
+    }
+}
+
+int launch_fused(physad_ctx* c, const physad_grid* g, const physad_slab& s, float t, float dt, double* acc,
+                 float* const R[4], cudaStream_t st) {
+    if (s.z_end == s.z_begin) {  // empty slab: the sum over nothing
+        CU(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+        return 0;
+    }
+    const float ts[3] = {t - dt, t, t + dt};  // as src/mlp_grid.cpp:87-89
+    const float tc[3] = {time_coord(ts[0], c->cfg.norm), time_coord(ts[1], c->cfg.norm), time_coord(ts[2], c->cfg.norm)};
+    switch (template_h(c->cfg.H)) {
+        case 32: return launch_fused_h<32>(c, g, s, tc, dt, acc, R, st);
+        case 64: return launch_fused_h<64>(c, g, s, tc, dt, acc, R, st);
+        case 128: return launch_fused_h<128>(c, g, s, tc, dt, acc, R, st);
+    }
+    return fail(PHYSAD_E_UNSUPPORTED, "H > 128 not built");
+}
+
+// ---- MLP over the grid ---------------------------------------------------------------------
+template <int H, bool FIELDS>
+int launch_grid_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], const GridInferArgs& a,
+                  cudaStream_t st) {
+    const size_t n = size_t(s.z_end - s.z_begin) * g->ny * g->nx;
+    if (n == 0) return 0;
+    MlpConst<H> k;
+    fill_const<H>(c, tc, k);
+    k_mlp_grid<H, FIELDS, 4><<<unsigned((n + 255) / 256), 256, 0, st>>>(k, a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <bool FIELDS>
+int launch_grid(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], GridInferArgs a,
+                cudaStream_t st) {
+    a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
+    a.z_begin = s.z_begin; a.z_end = s.z_end;
+    a.m1p1 = c->cfg.norm == 1;
+    switch (template_h(c->cfg.H)) {
+        case 32: return launch_grid_t<32, FIELDS>(c, g, s, tc, a, st);
+        case 64: return launch_grid_t<64, FIELDS>(c, g, s, tc, a, st);
+        case 128: return launch_grid_t<128, FIELDS>(c, g, s, tc, a, st);
+    }
+    return fail(PHYSAD_E_UNSUPPORTED, "H > 128 not built");
+}
+
+// ---- physics on supplied fields --------------------------------------------------------------
+template <bool WRITE_R, bool REDUCE, bool SCALE>
+int launch_phys(physad_ctx* c, const physad_grid* g, PhysArgs a, cudaStream_t st) {
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    const size_t blocks = (N + 255) / 256;
+    a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.periodic = g->periodic != 0;
+    a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
+    if (REDUCE) {
+        if (int rc = ensure_partials(c, blocks)) return rc;
+        a.partials = c->partials; a.ticket = c->ticket;
+    }
+    k_phys_residual<WRITE_R, REDUCE, SCALE><<<unsigned(blocks), 256, 0, st>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+PhysArgs phys_args(const float* s_m, const float* s_0, const float* s_p, const float* u_m, const float* u_0,
+                   const float* u_p, float* r0, float* r1, float* r2, float* r3) {
+    PhysArgs a{};
+    a.s_m = s_m; a.s_0 = s_0; a.s_p = s_p; a.u_m = u_m; a.u_0 = u_0; a.u_p = u_p;
+    a.R[0] = r0; a.R[1] = r1; a.R[2] = r2; a.R[3] = r3;
+    return a;
+}
+
+// VJP scales formed in fp32 exactly as src/phys_cpu.cpp:162-163
+void vjp_scales(const physad_grid* g, const physad_phys_weights* w, float* ss, float* su) {
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    *ss = 2.f * w->w_sigma / float(N);
+    *su = 2.f * w->w_u / float(N);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int physad_abi_version(void) { return PHYSAD_ABI_VERSION; }
+const char* physad_last_error(void) { return g_err.c_str(); }
+const char* physad_error_string(int status) {
+    switch (status) {
+        case PHYSAD_OK: return "ok";
+        case PHYSAD_E_INVALID: return "invalid argument";
+        case PHYSAD_E_UNSUPPORTED: return "unsupported shape";
+        case PHYSAD_E_NOWEIGHTS: return "no weights set";
+    }
+    return status > 0 ? cudaGetErrorString(cudaError_t(status)) : "unknown";
+}
+
+int physad_ctx_create(physad_ctx** out, int device) {
+    if (!out) return fail(PHYSAD_E_INVALID, "out is null");
+    *out = nullptr;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail(int(cudaErrorNoDevice), "no CUDA device: this library has no CPU fallback");
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= ndev) return fail(PHYSAD_E_INVALID, "device index out of range");
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+        return fail(PHYSAD_E_UNSUPPORTED, std::string("built for sm_100a only; device is sm_") + std::to_string(p.major) +
+                                              std::to_string(p.minor));
+    DeviceGuard dg(device);
+    physad_ctx* c = new physad_ctx();
+    c->device = device;
+    c->sm_count = p.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->ticket, sizeof(unsigned int)));
+    CU(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_acc, 2 * sizeof(double)));
+    CU(cudaMallocHost(&c->h_acc, 2 * sizeof(double)));
+    *out = c;
+    return 0;
+}
+
+int physad_ctx_destroy(physad_ctx* c) {
+    if (!c) return 0;
+    DeviceGuard dg(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->dW1); cudaFree(c->db1); cudaFree(c->dW2); cudaFree(c->db2);
+    cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_acc); cudaFree(c->scratch);
+    cudaFreeHost(c->h_acc);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int physad_ctx_sm_count(const physad_ctx* c) { return c ? c->sm_count : 0; }
+uint64_t physad_launch_count(const physad_ctx* c) { return c ? c->launches : 0; }
+int physad_set_fused_variant(physad_ctx* c, int v) {
+    if (!c) return -1;
+    const int prev = c->fused_variant;
+    c->fused_variant = v;
+    return prev;
+}
+
+int physad_set_weights(physad_ctx* c, const physad_mlp_config* cfg, const float* W1, const float* b1, const float* W2,
+                       const float* b2) {
+    if (!c || !cfg || !W1 || !b1 || !W2 || !b2) return fail(PHYSAD_E_INVALID, "set_weights: null argument");
+    if (cfg->In <= 0 || cfg->H <= 0 || cfg->Out <= 0) return fail(PHYSAD_E_INVALID, "set_weights: dims must be positive");
+    if (cfg->norm != 0 && cfg->norm != 1) return fail(PHYSAD_E_INVALID, "set_weights: norm must be 0 or 1");
+    DeviceGuard dg(c->device);
+    c->cfg = *cfg;
+    const size_t n[4] = {size_t(cfg->H) * cfg->In, size_t(cfg->H), size_t(cfg->Out) * cfg->H, size_t(cfg->Out)};
+    const float* src[4] = {W1, b1, W2, b2};
+    std::vector<float>* host[4] = {&c->W1, &c->b1, &c->W2, &c->b2};
+    float** dev[4] = {&c->dW1, &c->db1, &c->dW2, &c->db2};
+    for (int k = 0; k < 4; ++k) {
+        host[k]->assign(src[k], src[k] + n[k]);
+        if (n[k] > c->dW_cap[k]) {
+            if (*dev[k]) CU(cudaFree(*dev[k]));
+            *dev[k] = nullptr;
+            CU(cudaMalloc(dev[k], n[k] * sizeof(float)));
+            c->dW_cap[k] = n[k];
+        }
+        // host vector is owned by the context and outlives the copy
+        CU(cudaMemcpyAsync(*dev[k], host[k]->data(), n[k] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->has_weights = true;
+    return 0;
+}
+
+// ---- MLP operator -----------------------------------------------------------------------------
+int physad_mlp_forward_dev(physad_ctx* c, const float* x, float* y, size_t B, void* stream) {
+    if (!c || (B && (!x || !y))) return fail(PHYSAD_E_INVALID, "mlp_forward: null argument");
+    if (!c->has_weights) return fail(PHYSAD_E_NOWEIGHTS, "mlp_forward: no weights set");
+    if (B == 0) return 0;
+    DeviceGuard dg(c->device);
+    cudaStream_t st = cudaStream_t(stream);
+    const int In = c->cfg.In, H = c->cfg.H, Out = c->cfg.Out;
+    const size_t smem4 = size_t(H) * (2 * sizeof(float4) + sizeof(float));
+    if (In == 4 && Out == 4 && smem4 <= 200 * 1024 && (uintptr_t(x) % 16 == 0) && (uintptr_t(y) % 16 == 0)) {
+        if (smem4 > 48 * 1024)
+            CU(cudaFuncSetAttribute(k_mlp_forward_4x4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem4)));
+        k_mlp_forward_4x4<<<unsigned((B + 255) / 256), 256, smem4, st>>>(
+            reinterpret_cast<const float4*>(x), c->dW1, c->db1, c->dW2, c->db2, reinterpret_cast<float4*>(y), B, H);
+        c->launches++;
+    } else {
+        float* act = nullptr;
+        CU(cudaMallocAsync(&act, B * size_t(H) * sizeof(float), st));
+        k_mlp_generic_hidden<<<unsigned((B * size_t(H) + 255) / 256), 256, 0, st>>>(x, c->dW1, c->db1, act, B, In, H);
+        k_mlp_generic_out<<<unsigned((B * size_t(Out) + 255) / 256), 256, 0, st>>>(act, c->dW2, c->db2, y, B, H, Out);
+        c->launches += 2;
+        CU(cudaFreeAsync(act, st));
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int physad_mlp_forward_host(physad_ctx* c, const float* x, float* y, size_t B) {
+    if (!c || (B && (!x || !y))) return fail(PHYSAD_E_INVALID, "mlp_forward: null argument");
+    if (!c->has_weights) return fail(PHYSAD_E_NOWEIGHTS, "mlp_forward: no weights set");
+    if (B == 0) return 0;
+    DeviceGuard dg(c->device);
+    const size_t nx = B * size_t(c->cfg.In) * sizeof(float), ny = B * size_t(c->cfg.Out) * sizeof(float);
+    const size_t off_y = (nx + 255) & ~size_t(255);
+    if (int rc = ensure_scratch(c, off_y + ny)) return rc;
+    float* dx = reinterpret_cast<float*>(c->scratch);
+    float* dy = reinterpret_cast<float*>(c->scratch + off_y);
+    CU(cudaMemcpyAsync(dx, x, nx, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = physad_mlp_forward_dev(c, dx, dy, B, c->stream)) return rc;
+    CU(cudaMemcpyAsync(y, dy, ny, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int physad_mlp_grid_infer_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, float t, float* out,
+                              void* stream) {
+    if (!c || !out) return fail(PHYSAD_E_INVALID, "mlp_grid_infer: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = need_4x4(c, "mlp_grid_infer")) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    if (uintptr_t(out) % 16) return fail(PHYSAD_E_INVALID, "mlp_grid_infer: out must be 16-byte aligned");
+    DeviceGuard dg(c->device);
+    const float tcv = time_coord(t, c->cfg.norm);
+    const float tc[3] = {tcv, tcv, tcv};
+    GridInferArgs a{};
+    a.out_aos = reinterpret_cast<float4*>(out);
+    return launch_grid<false>(c, g, s, tc, a, cudaStream_t(stream));
+}
+
+int physad_mlp_grid_infer_host(physad_ctx* c, const physad_grid* g, float t, float* out) {
+    if (!c || !out) return fail(PHYSAD_E_INVALID, "mlp_grid_infer: null argument");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    const size_t bytes = size_t(g->nx) * g->ny * g->nz * 4 * sizeof(float);
+    if (int rc = ensure_scratch(c, bytes)) return rc;
+    if (int rc = physad_mlp_grid_infer_dev(c, g, nullptr, t, reinterpret_cast<float*>(c->scratch), c->stream)) return rc;
+    CU(cudaMemcpyAsync(out, c->scratch, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int physad_mlp_generate_fields_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, float t, float dt,
+                                   float* s_m, float* s_0, float* s_p, float* u_m, float* u_0, float* u_p, void* stream) {
+    if (!c || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p) return fail(PHYSAD_E_INVALID, "generate_fields: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = need_4x4(c, "generate_fields")) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    DeviceGuard dg(c->device);
+    const float ts[3] = {t - dt, t, t + dt};
+    const float tc[3] = {time_coord(ts[0], c->cfg.norm), time_coord(ts[1], c->cfg.norm), time_coord(ts[2], c->cfg.norm)};
+    GridInferArgs a{};
+    a.sigma[0] = s_m; a.sigma[1] = s_0; a.sigma[2] = s_p;
+    a.u[0] = u_m; a.u[1] = u_0; a.u[2] = u_p;
+    return launch_grid<true>(c, g, s, tc, a, cudaStream_t(stream));
+}
+
+int physad_mlp_generate_fields_host(physad_ctx* c, const physad_grid* g, float t, float dt, float* s_m, float* s_0,
+                                    float* s_p, float* u_m, float* u_0, float* u_p) {
+    if (!c) return fail(PHYSAD_E_INVALID, "generate_fields: null context");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    if (int rc = ensure_scratch(c, 12 * N * sizeof(float))) return rc;
+    float* d = reinterpret_cast<float*>(c->scratch);
+    if (int rc = physad_mlp_generate_fields_dev(c, g, nullptr, t, dt, d, d + N, d + 2 * N, d + 3 * N, d + 6 * N, d + 9 * N,
+                                                c->stream))
+        return rc;
+    float* dst[6] = {s_m, s_0, s_p, u_m, u_0, u_p};
+    const size_t off[6] = {0, N, 2 * N, 3 * N, 6 * N, 9 * N}, cnt[6] = {N, N, N, 3 * N, 3 * N, 3 * N};
+    for (int k = 0; k < 6; ++k)
+        CU(cudaMemcpyAsync(dst[k], d + off[k], cnt[k] * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- physics on supplied fields ------------------------------------------------------------------
+int physad_phys_residuals_dev(physad_ctx* c, const physad_grid* g, const float* s_m, const float* s_0, const float* s_p,
+                              const float* u_m, const float* u_0, const float* u_p, float* Rs, float* Rx, float* Ry,
+                              float* Rz, void* stream) {
+    if (!c || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p || !Rs || !Rx || !Ry || !Rz)
+        return fail(PHYSAD_E_INVALID, "phys_residuals: null argument");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    return launch_phys<true, false, false>(c, g, phys_args(s_m, s_0, s_p, u_m, u_0, u_p, Rs, Rx, Ry, Rz), cudaStream_t(stream));
+}
+
+int physad_phys_loss_dev(physad_ctx* c, const physad_grid* g, const float* s_m, const float* s_0, const float* s_p,
+                         const float* u_m, const float* u_0, const float* u_p, double* acc, float* Rs, float* Rx,
+                         float* Ry, float* Rz, void* stream) {
+    if (!c || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p || !acc) return fail(PHYSAD_E_INVALID, "phys_loss: null argument");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    PhysArgs a = phys_args(s_m, s_0, s_p, u_m, u_0, u_p, Rs, Rx, Ry, Rz);
+    a.acc_out = acc;
+    if (Rs || Rx || Ry || Rz) return launch_phys<true, true, false>(c, g, a, cudaStream_t(stream));
+    return launch_phys<false, true, false>(c, g, a, cudaStream_t(stream));
+}
+
+int physad_phys_backward_dev(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w, const float* Rs,
+                             const float* Rx, const float* Ry, const float* Rz, float* gs, float* gx, float* gy,
+                             float* gz, void* stream) {
+    if (!c || !w || !Rs || !Rx || !Ry || !Rz || !gs || !gx || !gy || !gz)
+        return fail(PHYSAD_E_INVALID, "phys_backward: null argument");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    ScaleArgs a{};
+    float ss, su;
+    vjp_scales(g, w, &ss, &su);
+    a.R[0] = Rs; a.R[1] = Rx; a.R[2] = Ry; a.R[3] = Rz;
+    a.G[0] = gs; a.G[1] = gx; a.G[2] = gy; a.G[3] = gz;
+    a.scale[0] = ss; a.scale[1] = a.scale[2] = a.scale[3] = su;
+    a.n = size_t(g->nx) * g->ny * g->nz;
+    int vec4 = (a.n % 4 == 0);
+    for (int k = 0; k < 4; ++k) vec4 = vec4 && (uintptr_t(a.R[k]) % 16 == 0) && (uintptr_t(a.G[k]) % 16 == 0);
+    const size_t work = vec4 ? a.n / 4 : a.n;
+    const unsigned blocks = unsigned(std::min<size_t>((work + 255) / 256, size_t(c->sm_count) * 16));
+    k_scale4<<<std::max(1u, blocks), 256, 0, cudaStream_t(stream)>>>(a, vec4);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int physad_phys_backward_from_fields_dev(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w,
+                                         const float* s_m, const float* s_0, const float* s_p, const float* u_m,
+                                         const float* u_0, const float* u_p, float* gs, float* gx, float* gy, float* gz,
+                                         void* stream) {
+    if (!c || !w || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p || !gs || !gx || !gy || !gz)
+        return fail(PHYSAD_E_INVALID, "phys_backward_from_fields: null argument");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    PhysArgs a = phys_args(s_m, s_0, s_p, u_m, u_0, u_p, gs, gx, gy, gz);
+    vjp_scales(g, w, &a.scale_s, &a.scale_u);
+    return launch_phys<true, false, true>(c, g, a, cudaStream_t(stream));
+}
+
+// Host-pointer forms: stage 12N floats in, run, stage results out (the reference API's contract,
+// include/phys.h:66, minus its per-call cudaMalloc/cudaFree: scratch is kept by the context).
+namespace {
+int upload_fields(physad_ctx* c, size_t N, const float* const src[6], float** d_out) {
+    if (int rc = ensure_scratch(c, 16 * N * sizeof(float))) return rc;
+    float* d = reinterpret_cast<float*>(c->scratch);
+    const size_t off[6] = {0, N, 2 * N, 3 * N, 6 * N, 9 * N}, cnt[6] = {N, N, N, 3 * N, 3 * N, 3 * N};
+    for (int k = 0; k < 6; ++k)
+        CU(cudaMemcpyAsync(d + off[k], src[k], cnt[k] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    *d_out = d;
+    return 0;
+}
+}  // namespace
+
+int physad_phys_residuals_host(physad_ctx* c, const physad_grid* g, const float* s_m, const float* s_0, const float* s_p,
+                               const float* u_m, const float* u_0, const float* u_p, float* Rs, float* Rx, float* Ry,
+                               float* Rz, float* kernel_ms) {
+    if (!c || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p || !Rs || !Rx || !Ry || !Rz)
+        return fail(PHYSAD_E_INVALID, "phys_residuals: null argument");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    const float* src[6] = {s_m, s_0, s_p, u_m, u_0, u_p};
+    float* d;
+    if (int rc = upload_fields(c, N, src, &d)) return rc;
+    float* r = d + 12 * N;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) {
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, c->stream));
+    }
+    if (int rc = physad_phys_residuals_dev(c, g, d, d + N, d + 2 * N, d + 3 * N, d + 6 * N, d + 9 * N, r, r + N, r + 2 * N,
+                                           r + 3 * N, c->stream))
+        return rc;
+    if (kernel_ms) CU(cudaEventRecord(e1, c->stream));
+    float* dst[4] = {Rs, Rx, Ry, Rz};
+    for (int k = 0; k < 4; ++k)
+        CU(cudaMemcpyAsync(dst[k], r + k * N, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (kernel_ms) {
+        CU(cudaEventElapsedTime(kernel_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return 0;
+}
+
+int physad_phys_loss_host(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w, const float* s_m,
+                          const float* s_0, const float* s_p, const float* u_m, const float* u_0, const float* u_p,
+                          float* loss_sigma, float* loss_u, float* Rs, float* Rx, float* Ry, float* Rz) {
+    if (!c || !w || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p) return fail(PHYSAD_E_INVALID, "phys_loss: null argument");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    const float* src[6] = {s_m, s_0, s_p, u_m, u_0, u_p};
+    float* d;
+    if (int rc = upload_fields(c, N, src, &d)) return rc;
+    float* r = d + 12 * N;
+    float* host_r[4] = {Rs, Rx, Ry, Rz};
+    float* dev_r[4];
+    for (int k = 0; k < 4; ++k) dev_r[k] = host_r[k] ? r + k * N : nullptr;
+    if (int rc = physad_phys_loss_dev(c, g, d, d + N, d + 2 * N, d + 3 * N, d + 6 * N, d + 9 * N, c->d_acc, dev_r[0],
+                                      dev_r[1], dev_r[2], dev_r[3], c->stream))
+        return rc;
+    CU(cudaMemcpyAsync(c->h_acc, c->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    for (int k = 0; k < 4; ++k)
+        if (host_r[k]) CU(cudaMemcpyAsync(host_r[k], dev_r[k], N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    physad_finalize_loss(c->h_acc, w, N, loss_sigma, loss_u);
+    return 0;
+}
+
+int physad_phys_backward_host(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w, const float* Rs,
+                              const float* Rx, const float* Ry, const float* Rz, float* gs, float* gx, float* gy,
+                              float* gz) {
+    if (!c || !w || !Rs || !Rx || !Ry || !Rz || !gs || !gx || !gy || !gz)
+        return fail(PHYSAD_E_INVALID, "phys_backward: null argument");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    if (int rc = ensure_scratch(c, 8 * N * sizeof(float))) return rc;
+    float* d = reinterpret_cast<float*>(c->scratch);
+    const float* src[4] = {Rs, Rx, Ry, Rz};
+    float* dst[4] = {gs, gx, gy, gz};
+    for (int k = 0; k < 4; ++k)
+        CU(cudaMemcpyAsync(d + k * N, src[k], N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    float* o = d + 4 * N;
+    if (int rc = physad_phys_backward_dev(c, g, w, d, d + N, d + 2 * N, d + 3 * N, o, o + N, o + 2 * N, o + 3 * N, c->stream))
+        return rc;
+    for (int k = 0; k < 4; ++k)
+        CU(cudaMemcpyAsync(dst[k], o + k * N, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int physad_phys_backward_from_fields_host(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w,
+                                          const float* s_m, const float* s_0, const float* s_p, const float* u_m,
+                                          const float* u_0, const float* u_p, float* gs, float* gx, float* gy, float* gz) {
+    if (!c || !w || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p || !gs || !gx || !gy || !gz)
+        return fail(PHYSAD_E_INVALID, "phys_backward_from_fields: null argument");
+    if (int rc = check_grid(g)) return rc;
+    DeviceGuard dg(c->device);
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    const float* src[6] = {s_m, s_0, s_p, u_m, u_0, u_p};
+    float* d;
+    if (int rc = upload_fields(c, N, src, &d)) return rc;
+    float* o = d + 12 * N;
+    if (int rc = physad_phys_backward_from_fields_dev(c, g, w, d, d + N, d + 2 * N, d + 3 * N, d + 6 * N, d + 9 * N, o, o + N,
+                                                      o + 2 * N, o + 3 * N, c->stream))
+        return rc;
+    float* dst[4] = {gs, gx, gy, gz};
+    for (int k = 0; k < 4; ++k)
+        CU(cudaMemcpyAsync(dst[k], o + k * N, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- the metric path ---------------------------------------------------------------------------------
+int physad_fused_loss_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, float t, float dt, double* acc,
+                          float* Rs, float* Rx, float* Ry, float* Rz, void* stream) {
+    if (!c || !acc) return fail(PHYSAD_E_INVALID, "fused_loss: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = need_4x4(c, "fused_loss")) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    const bool any = Rs || Rx || Ry || Rz, all = Rs && Rx && Ry && Rz;
+    if (any && !all) return fail(PHYSAD_E_INVALID, "fused_loss: residual outputs must be all set or all null");
+    DeviceGuard dg(c->device);
+    float* R[4] = {Rs, Rx, Ry, Rz};
+    return launch_fused(c, g, s, t, dt, acc, R, cudaStream_t(stream));
+}
+
+int physad_fused_loss_host(physad_ctx* c, const physad_grid* g, const physad_mlp_config* cfg, const float* W1,
+                           const float* b1, const float* W2, const float* b2, const physad_phys_weights* w, float t,
+                           float dt, float* loss_sigma, float* loss_u, float* Rs, float* Rx, float* Ry, float* Rz) {
+    if (!c || !w) return fail(PHYSAD_E_INVALID, "fused_loss: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (cfg) {
+        if (int rc = physad_set_weights(c, cfg, W1, b1, W2, b2)) return rc;
+    }
+    DeviceGuard dg(c->device);
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    float* host_r[4] = {Rs, Rx, Ry, Rz};
+    const bool want_r = Rs || Rx || Ry || Rz;
+    float* r = nullptr;
+    if (want_r) {
+        if (int rc = ensure_scratch(c, 4 * N * sizeof(float))) return rc;
+        r = reinterpret_cast<float*>(c->scratch);
+    }
+    if (int rc = physad_fused_loss_dev(c, g, nullptr, t, dt, c->d_acc, r, r ? r + N : nullptr, r ? r + 2 * N : nullptr,
+                                       r ? r + 3 * N : nullptr, c->stream))
+        return rc;
+    CU(cudaMemcpyAsync(c->h_acc, c->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    for (int k = 0; k < 4; ++k)
+        if (host_r[k]) CU(cudaMemcpyAsync(host_r[k], r + k * N, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    physad_finalize_loss(c->h_acc, w, N, loss_sigma, loss_u);
+    return 0;
+}
+
+void physad_finalize_loss(const double acc[2], const physad_phys_weights* w, size_t n_global, float* loss_sigma,
+                          float* loss_u) {
+    const double invN = 1.0 / double(n_global);
+    if (loss_sigma) *loss_sigma = float(double(w->w_sigma) * acc[0] * invN);
+    if (loss_u) *loss_u = float(double(w->w_u) * acc[1] * invN);
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+// The metric kernel: fused coordinate-MLP evaluation + central-difference PDE residual + loss
+// reduction for a z-slab of the grid, one launch, nothing but 16 bytes leaves the chip.
+//
+// Work decomposition
+//   block  = one (TX x TY) tile of (x,y) columns x one chunk of z planes; it MARCHES along z.
+//   thread = P columns that share x (rows ty, ty+TYB, ...); 32 lanes of a warp = 32 consecutive x.
+//   step k = plane zk = chunk_begin - 1 + k.  Interior steps evaluate all three time slices for
+//            the thread's columns (sharing the layer-1 prefix, see mlp_eval.cuh); the first and the
+//            last step are the chunk's z-halo and evaluate time t only.
+//   halo   = the stencil is the 7-point cross, so besides the tile only the ring of 2(TX+TY)
+//            columns around it is needed at time t.  Ring columns are recomputed from coordinates
+//            (the MLP is a pure function of (x,y,z,t): SURVEY.md section 8e) in 32-column tasks that
+//            rotate over the block's warps from plane to plane so no warp/SMSP is the slow one.
+//   fields = time-t outputs of the last four planes live in shared memory ([4 planes][4 ch]
+//            [(TY+2) x (TX+2)]); the time differences (y(t+dt) - y(t-dt)) / (2 dt) of the plane whose
+//            residual is pending stay in registers.  One __syncthreads per plane.
+//   residual (plane zk-1, formed at step k when plane zk is known): reference src/phys_cpu.cpp:66-109
+//            in fp32 (the reference's own CUDA kernels are fp32 too, src/phys_cuda_fused.cu:67-99);
+//            squares are accumulated per thread in double exactly like src/phys_cpu.cpp:140-145,
+//            then warp shuffle -> block -> per-block partial -> last block sums partials in index order
+//            (deterministic for a given launch geometry).
+// Out-of-range columns of partial tiles evaluate at the wrapped/clamped coordinate, which is what
+// their in-range neighbours need as halo; they just never contribute to the sum.
+#pragma once
+#include "mlp_eval.cuh"
+
+namespace physad {
+
+struct FusedArgs {
+    int nx, ny, nz;          // global grid
+    int z_begin, z_end;      // slab [z_begin, z_end)
+    int tiles_x, tiles_y, nchunks;
+    int m1p1, periodic;
+    float inv2dt, inv2hx, inv2hy, inv2hz;
+    double2* partials;       // [gridDim.x]
+    unsigned int* ticket;    // zero on entry, zero again on exit
+    double* acc_out;         // [2]
+    float* R[4];             // slab-local residual outputs or null
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide {a,b} sum -> per-block partial -> grid total written by the last block to finish.
+template <int NWARPS>
+__device__ __forceinline__ void grid_reduce2(double a, double b, double2* partials, unsigned int* ticket, double* out,
+                                             double2* s_red, unsigned int* s_flag) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) s_red[wid] = make_double2(a, b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int i = 0; i < NWARPS; ++i) { sa += s_red[i].x; sb += s_red[i].y; }
+        partials[blockIdx.x] = make_double2(sa, sb);
+        __threadfence();
+        *s_flag = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    if (*s_flag != gridDim.x - 1) return;
+    // last block: fixed-order strided sums, then the same tree
+    __threadfence();
+    double sa = 0.0, sb = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += NWARPS * 32) {
+        const double2 p = __ldcg(&partials[i]);
+        sa += p.x; sb += p.y;
+    }
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    __syncthreads();
+    if (lane == 0) s_red[wid] = make_double2(sa, sb);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0;
+#pragma unroll
+        for (int i = 0; i < NWARPS; ++i) { ta += s_red[i].x; tb += s_red[i].y; }
+        out[0] = ta;
+        out[1] = tb;
+        *ticket = 0u;
+    }
+}
+
+template <int H, int P, int TYB, int UNROLL, int MINB>
+__global__ void __launch_bounds__(32 * TYB, MINB)
+k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) {
+    constexpr int TX = 32, TY = TYB * P, NWARPS = TYB;
+    constexpr int SX = TX + 2, SY = TY + 2, CH = SX * SY, PLANE = 4 * CH, NB = 4;
+    constexpr int RING = 2 * TX + 2 * TY, NTASK = (RING + 31) / 32;
+    extern __shared__ float smem[];
+    float* buf = smem;  // [NB][4][SY][SX]
+    __shared__ double2 s_red[NWARPS];
+    __shared__ unsigned int s_flag;
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // warp id == ty
+    const bool m1p1 = a.m1p1 != 0, per = a.periodic != 0;
+
+    int b = blockIdx.x;
+    const int tile_x = b % a.tiles_x; b /= a.tiles_x;
+    const int tile_y = b % a.tiles_y; b /= a.tiles_y;
+    const int chunk = b;
+    const int nzl = a.z_end - a.z_begin;
+    const int zc0 = a.z_begin + int((long long)chunk * nzl / a.nchunks);
+    const int zc1 = a.z_begin + int((long long)(chunk + 1) * nzl / a.nchunks);
+    const int nplanes = zc1 - zc0;
+    const int x0 = tile_x * TX, y0 = tile_y * TY;
+
+    // this thread's columns
+    const int gx = x0 + tx;
+    const float cx = axis_coord(bc_index(gx, a.nx, per), a.nx, m1p1);
+    float cy[P];
+    bool live[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int gy = y0 + ty + j * TYB;
+        cy[j] = axis_coord(bc_index(gy, a.ny, per), a.ny, m1p1);
+        live[j] = gx < a.nx && gy < a.ny;
+    }
+    // this lane's ring columns (one per task), fixed for the whole march
+    float rcx[NTASK], rcy[NTASK];
+    int roff[NTASK];
+#pragma unroll
+    for (int i = 0; i < NTASK; ++i) {
+        const int r = i * 32 + tx;
+        int xx, yy;
+        if (r < TX) { xx = 1 + r; yy = 0; }
+        else if (r < 2 * TX) { xx = 1 + r - TX; yy = SY - 1; }
+        else if (r < 2 * TX + TY) { xx = 0; yy = 1 + r - 2 * TX; }
+        else { xx = SX - 1; yy = 1 + r - 2 * TX - TY; }
+        if (r >= RING) { xx = 0; yy = 0; }  // idle lane of the last task: harmless duplicate slot
+        rcx[i] = axis_coord(bc_index(x0 - 1 + xx, a.nx, per), a.nx, m1p1);
+        rcy[i] = axis_coord(bc_index(y0 - 1 + yy, a.ny, per), a.ny, m1p1);
+        roff[i] = (r < RING) ? yy * SX + xx : -1;
+    }
+
+    float dT[P][4];  // time derivative of the plane whose residual is pending
+#pragma unroll
+    for (int j = 0; j < P; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dT[j][c] = 0.f;
+    double acc_s = 0.0, acc_u = 0.0;
+
+    for (int k = 0; k <= nplanes + 1; ++k) {
+        const int zk = zc0 - 1 + k;
+        const float cz = axis_coord(bc_index(zk, a.nz, per), a.nz, m1p1);
+        float* pl = buf + (k & (NB - 1)) * PLANE;
+        const bool halo_plane = (k == 0) || (k == nplanes + 1);
+        float dTn[P][4];
+        if (halo_plane) {
+            float y[P][1][4];
+            mlp_eval<H, 1, P, UNROLL>(w, cx, cy, cz, y);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const int o = (1 + ty + j * TYB) * SX + 1 + tx;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { pl[c * CH + o] = y[j][0][c]; dTn[j][c] = 0.f; }
+            }
+        } else {
+            float y[P][3][4];
+            mlp_eval<H, 3, P, UNROLL>(w, cx, cy, cz, y);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const int o = (1 + ty + j * TYB) * SX + 1 + tx;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    pl[c * CH + o] = y[j][1][c];
+                    dTn[j][c] = central_diff(y[j][2][c], y[j][0][c], a.inv2dt);
+                }
+            }
+            // ring duty for this plane (x/y neighbours of the tile edge), rotating over warps
+#pragma unroll
+            for (int i = 0; i < NTASK; ++i) {
+                if ((i + k) % NWARPS == ty) {
+                    float yr[1][1][4];
+                    const float rc[1] = {rcy[i]};
+                    mlp_eval<H, 1, 1, UNROLL>(w, rcx[i], rc, cz, yr);
+                    if (roff[i] >= 0) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) pl[c * CH + roff[i]] = yr[0][0][c];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (k >= 2) {
+            // residual of plane zk-1: centre/x/y neighbours from plane buffer k-1, z neighbours from k-2 and k
+            const float* pc = buf + ((k - 1) & (NB - 1)) * PLANE;
+            const float* pm = buf + ((k - 2) & (NB - 1)) * PLANE;
+            const float* pp = pl;
+            const int zl = zk - 1 - a.z_begin;  // slab-local plane of the residual
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const int o = (1 + ty + j * TYB) * SX + 1 + tx;
+                float f[4], gxv[4], gyv[4], gzv[4], R[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float* q = pc + c * CH + o;
+                    f[c] = q[0];
+                    gxv[c] = central_diff(q[1], q[-1], a.inv2hx);
+                    gyv[c] = central_diff(q[SX], q[-SX], a.inv2hy);
+                    gzv[c] = central_diff(pp[c * CH + o], pm[c * CH + o], a.inv2hz);
+                }
+                point_residual(f, gxv, gyv, gzv, dT[j], R);
+                const float Rs = R[0], Rx = R[1], Ry = R[2], Rz = R[3];
+                if (live[j]) {
+                    acc_s += double(Rs) * double(Rs);
+                    acc_u += double(Rx) * double(Rx) + double(Ry) * double(Ry) + double(Rz) * double(Rz);
+                    if (a.R[0]) {
+                        const size_t i = (size_t(zl) * a.ny + (y0 + ty + j * TYB)) * a.nx + gx;
+                        a.R[0][i] = Rs; a.R[1][i] = Rx; a.R[2][i] = Ry; a.R[3][i] = Rz;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dT[j][c] = dTn[j][c];
+    }
+    grid_reduce2<NWARPS>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag);
+}
+
+}  // namespace physad

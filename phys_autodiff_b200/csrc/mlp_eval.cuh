@@ -1,0 +1,112 @@
+// Strict-fp32 evaluation of the reference's two-layer coordinate MLP, written for sm_100a.
+//
+// "Strict" = every multiply and every add is rounded separately (__fmul_rn / __fadd_rn, which nvcc
+// never contracts into FFMA) and accumulated in the reference's order, so the outputs are
+// bit-identical to mlp_forward<ExecCpu> (reference src/mlp_cpu.cpp:14-36):
+//     a[h] = relu(b1[h] + W1[h,0]*x + W1[h,1]*y + W1[h,2]*z + W1[h,3]*t)     (left to right)
+//     y[o] = b2[o] + sum_{h ascending} W2[o,h]*a[h]
+// SURVEY.md section 0 fact 3 explains why this matters: the time difference multiplies output
+// noise by 1/(2 dt), so FFMA-contracted outputs break the 1e-5 residual tolerance.
+//
+// What is shared instead of recomputed (none of it changes a single rounding):
+//   * the three time slices t-dt, t, t+dt differ only in the LAST layer-1 term, so the prefix
+//     ((b1 + W1[h,0]*x) + W1[h,1]*y) + W1[h,2]*z is computed once and the pre-rounded products
+//     W1[h,3]*t_slice (the same for every grid point) are formed once on the host;
+//   * a thread's P points share x (and the plane's z), so b1 + W1[h,0]*x and W1[h,2]*z are
+//     computed once per thread.
+// Weights arrive through the kernel-parameter constant bank (MlpConst is a __grid_constant__
+// argument): uniform loads, no shared-memory or LSU traffic in the inner loop.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace physad {
+
+// Per-hidden-unit records, laid out for 128-bit uniform loads.
+template <int H>
+struct MlpConst {
+    float4 l1[H];  // {b1[h], W1[h,0], W1[h,1], W1[h,2]}
+    float4 lt[H];  // {W1[h,3]*t_minus, W1[h,3]*t_0, W1[h,3]*t_plus, 0}   (rounded fp32 products)
+    float4 w2[H];  // {W2[0,h], W2[1,h], W2[2,h], W2[3,h]}
+    float4 b2;     // {b2[0..3]}
+};
+
+__device__ __forceinline__ float relu_ref(float s) {
+    // reference: s > 0 ? s : 0 (src/mlp_cpu.cpp:7-9).  fmaxf gives the same value for every input
+    // (NaN -> 0 as well); only the sign of a zero result may differ.
+    return fmaxf(s, 0.f);
+}
+
+// Axis coordinate of grid index i (reference src/mlp_grid.cpp:25-29): IEEE division, then 2u-1.
+__device__ __forceinline__ float axis_coord(int i, int n, bool m1p1) {
+    if (n <= 1) return 0.f;
+    const float u = __fdiv_rn(float(i), float(n - 1));
+    return m1p1 ? __fsub_rn(__fmul_rn(2.f, u), 1.f) : u;
+}
+
+// Neighbour index rule of the stencil (reference src/phys_cpu.cpp:8-15): wrap or clamp.
+__device__ __forceinline__ int bc_index(int v, int n, bool periodic) {
+    if (periodic) {
+        int r = v % n;
+        return r < 0 ? r + n : r;
+    }
+    return v < 0 ? 0 : (v > n - 1 ? n - 1 : v);
+}
+
+// NS = 3: all three time slices (y[j][0|1|2] = t-dt | t | t+dt);  NS = 1: time t only (y[j][0]).
+// P points share cx and cz and differ in cy.
+template <int H, int NS, int P, int UNROLL>
+__device__ __forceinline__ void mlp_eval(const MlpConst<H>& w, float cx, const float (&cy)[P], float cz,
+                                         float (&y)[P][NS][4]) {
+    const float4 b2 = w.b2;
+#pragma unroll
+    for (int j = 0; j < P; ++j)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            y[j][s][0] = b2.x; y[j][s][1] = b2.y; y[j][s][2] = b2.z; y[j][s][3] = b2.w;
+        }
+#pragma unroll UNROLL
+    for (int h = 0; h < H; ++h) {
+        const float4 a = w.l1[h];
+        const float4 tt = w.lt[h];
+        const float4 c = w.w2[h];
+        const float sx = __fadd_rn(a.x, __fmul_rn(a.y, cx));  // b1 + W1[h,0]*x
+        const float mz = __fmul_rn(a.w, cz);                  // W1[h,2]*z
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const float sxyz = __fadd_rn(__fadd_rn(sx, __fmul_rn(a.z, cy[j])), mz);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const float pt = (NS == 1) ? tt.y : (s == 0 ? tt.x : (s == 1 ? tt.y : tt.z));
+                const float act = relu_ref(__fadd_rn(sxyz, pt));
+                y[j][s][0] = __fadd_rn(y[j][s][0], __fmul_rn(c.x, act));
+                y[j][s][1] = __fadd_rn(y[j][s][1], __fmul_rn(c.y, act));
+                y[j][s][2] = __fadd_rn(y[j][s][2], __fmul_rn(c.z, act));
+                y[j][s][3] = __fadd_rn(y[j][s][3], __fmul_rn(c.w, act));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Point residual (reference src/phys_cpu.cpp:80-106), fp32 with every rounding spelled out so the
+// fused kernel and the stage-wise kernel produce identical bits from identical fields.
+//   f = [sigma, ux, uy, uz] at the point;  g?[c] = d f_c / d?;  dT[c] = d f_c / dt.
+// The CPU reference evaluates the same expressions in double; fp32 with fused multiply-adds stays
+// within ~1e-7 * max|R| of it, well inside the 1e-5 gate.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float central_diff(float plus, float minus, float inv2h) {
+    return __fmul_rn(__fsub_rn(plus, minus), inv2h);
+}
+
+__device__ __forceinline__ void point_residual(const float (&f)[4], const float (&gx)[4], const float (&gy)[4],
+                                               const float (&gz)[4], const float (&dT)[4], float (&R)[4]) {
+    const float div = __fadd_rn(__fadd_rn(gx[1], gy[2]), gz[3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float adv = __fmaf_rn(f[3], gz[c], __fmaf_rn(f[2], gy[c], __fmul_rn(f[1], gx[c])));
+        R[c] = __fadd_rn(dT[c], adv);
+    }
+    R[0] = __fmaf_rn(f[0], div, R[0]);
+}
+
+}  // namespace physad

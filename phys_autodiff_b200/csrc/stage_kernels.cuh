@@ -1,0 +1,218 @@
+// Stage-wise kernels behind the reference's existing operator names: MLP over a grid / over a
+// coordinate array (strict fp32, bit-exact with src/mlp_cpu.cpp), the finite-difference physics
+// residual on externally supplied fields with an on-device double reduction, and the residual VJP.
+// These are the device-resident, HBM-facing halves of the path; the metric kernel is in
+// fused_loss.cuh.
+#pragma once
+#include "fused_loss.cuh"
+
+namespace physad {
+
+// ---------------------------------------------------------------------------------------------
+// MLP over the grid, coordinates from the point index (reference: make_grid_coords +
+// mlp_forward, src/mlp_grid.cpp:21-43,53-67).  One thread per point of the slab.
+//   FIELDS = false: one time slice, AoS float4 [sigma,ux,uy,uz] per point (mlp_grid_infer_cuda).
+//   FIELDS = true : three slices t-dt,t,t+dt split into sigma[n] / u[3n] channel-major arrays
+//                   (mlp_generate_fields_cuda + split_outputs_to_fields, src/mlp_grid.cpp:69-106),
+//                   sharing the layer-1 prefix between the slices.
+// For FIELDS=false the single slice's time products are expected in lt[h].y.
+// ---------------------------------------------------------------------------------------------
+struct GridInferArgs {
+    int nx, ny, nz;
+    int z_begin, z_end;
+    int m1p1;
+    float4* out_aos;    // FIELDS=false
+    float* sigma[3];    // FIELDS=true: t-dt, t, t+dt
+    float* u[3];
+};
+
+template <int H, bool FIELDS, int UNROLL>
+__global__ void __launch_bounds__(256) k_mlp_grid(const __grid_constant__ MlpConst<H> w, const GridInferArgs a) {
+    const size_t n = size_t(a.z_end - a.z_begin) * a.ny * a.nx;
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = int(i % a.nx);
+    const size_t r = i / a.nx;
+    const int y = int(r % a.ny);
+    const int z = a.z_begin + int(r / a.ny);
+    const bool m1p1 = a.m1p1 != 0;
+    const float cx = axis_coord(x, a.nx, m1p1);
+    const float cy[1] = {axis_coord(y, a.ny, m1p1)};
+    const float cz = axis_coord(z, a.nz, m1p1);
+    if (FIELDS) {
+        float o[1][3][4];
+        mlp_eval<H, 3, 1, UNROLL>(w, cx, cy, cz, o);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            a.sigma[s][i] = o[0][s][0];
+            a.u[s][i] = o[0][s][1];
+            a.u[s][n + i] = o[0][s][2];
+            a.u[s][2 * n + i] = o[0][s][3];
+        }
+    } else {
+        float o[1][1][4];
+        mlp_eval<H, 1, 1, UNROLL>(w, cx, cy, cz, o);
+        a.out_aos[i] = make_float4(o[0][0][0], o[0][0][1], o[0][0][2], o[0][0][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MLP on an explicit coordinate/feature array, generic In/H/Out (mlp_forward<ExecCuda>,
+// include/mlp.h:5-6).  Weights are staged once per block in shared memory in their reference
+// layouts.  In = Out = 4 takes the register path; anything else goes through the two generic
+// kernels with a [B x H] activation scratch, like the reference's own layout (src/mlp_cpu.cpp:16).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mlp_forward_4x4(const float4* __restrict__ x, const float* __restrict__ W1,
+                                                         const float* __restrict__ b1, const float* __restrict__ W2,
+                                                         const float* __restrict__ b2, float4* __restrict__ y, size_t B,
+                                                         int H) {
+    extern __shared__ float4 sw[];  // [H] {b1,w0,w1,w2}, [H] {w3, W2[0..2][h]}, [H] {W2[3][h],..}
+    float4* s_a = sw;
+    float4* s_b = sw + H;
+    float* s_c = reinterpret_cast<float*>(sw + 2 * H);
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        s_a[h] = make_float4(b1[h], W1[h * 4 + 0], W1[h * 4 + 1], W1[h * 4 + 2]);
+        s_b[h] = make_float4(W1[h * 4 + 3], W2[h], W2[H + h], W2[2 * H + h]);
+        s_c[h] = W2[3 * H + h];
+    }
+    __syncthreads();
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float4 p = x[i];
+    float o0 = b2[0], o1 = b2[1], o2 = b2[2], o3 = b2[3];
+#pragma unroll 4
+    for (int h = 0; h < H; ++h) {
+        const float4 a = s_a[h], c = s_b[h];
+        const float d = s_c[h];
+        float s = __fadd_rn(a.x, __fmul_rn(a.y, p.x));
+        s = __fadd_rn(s, __fmul_rn(a.z, p.y));
+        s = __fadd_rn(s, __fmul_rn(a.w, p.z));
+        s = __fadd_rn(s, __fmul_rn(c.x, p.w));
+        const float act = relu_ref(s);
+        o0 = __fadd_rn(o0, __fmul_rn(c.y, act));
+        o1 = __fadd_rn(o1, __fmul_rn(c.z, act));
+        o2 = __fadd_rn(o2, __fmul_rn(c.w, act));
+        o3 = __fadd_rn(o3, __fmul_rn(d, act));
+    }
+    y[i] = make_float4(o0, o1, o2, o3);
+}
+
+__global__ void __launch_bounds__(256) k_mlp_generic_hidden(const float* __restrict__ x, const float* __restrict__ W1,
+                                                            const float* __restrict__ b1, float* __restrict__ act,
+                                                            size_t B, int In, int H) {
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= B * size_t(H)) return;
+    const size_t i = e / H;
+    const int h = int(e % H);
+    float s = b1[h];
+    for (int k = 0; k < In; ++k) s = __fadd_rn(s, __fmul_rn(W1[size_t(h) * In + k], x[i * In + k]));
+    act[e] = relu_ref(s);
+}
+
+__global__ void __launch_bounds__(256) k_mlp_generic_out(const float* __restrict__ act, const float* __restrict__ W2,
+                                                         const float* __restrict__ b2, float* __restrict__ y, size_t B,
+                                                         int H, int Out) {
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= B * size_t(Out)) return;
+    const size_t i = e / Out;
+    const int o = int(e % Out);
+    float s = b2[o];
+    for (int h = 0; h < H; ++h) s = __fadd_rn(s, __fmul_rn(W2[size_t(o) * H + h], act[i * H + h]));
+    y[e] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Physics residual on supplied fields (reference src/phys_cpu.cpp:25-110; fp32 like the reference's
+// CUDA kernels).  One thread per point; the 7-point cross is read through L1/L2 (x+-1 share the
+// centre's lines, y+-1 / z+-1 are L2 hits), so HBM sees each field once: 48 B in + 16 B out per point.
+//   WRITE_R : store the four residual arrays
+//   REDUCE  : accumulate {sum Rs^2, sum |Ru|^2} in double -> acc_out (on-device loss reduction)
+//   SCALE   : store scale_s*Rs, scale_u*Ru instead of R (backward recomputed from fields,
+//             cuda_phys_loss_backward_fused, include/phys.h:132-143)
+// ---------------------------------------------------------------------------------------------
+struct PhysArgs {
+    int nx, ny, nz;
+    int periodic;
+    float inv2dt, inv2hx, inv2hy, inv2hz;
+    float scale_s, scale_u;
+    const float* s_m; const float* s_0; const float* s_p;
+    const float* u_m; const float* u_0; const float* u_p;
+    float* R[4];
+    double2* partials; unsigned int* ticket; double* acc_out;
+};
+
+template <bool WRITE_R, bool REDUCE, bool SCALE>
+__global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
+    __shared__ double2 s_red[8];
+    __shared__ unsigned int s_flag;
+    const size_t N = size_t(a.nx) * a.ny * a.nz;
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    double acc_s = 0.0, acc_u = 0.0;
+    if (i < N) {
+        const bool per = a.periodic != 0;
+        const int x = int(i % a.nx);
+        const size_t r = i / a.nx;
+        const int y = int(r % a.ny), z = int(r / a.ny);
+        const size_t row = size_t(a.nx), pln = size_t(a.nx) * a.ny;
+        const size_t ixp = i - x + bc_index(x + 1, a.nx, per), ixm = i - x + bc_index(x - 1, a.nx, per);
+        const size_t iyp = i + (ptrdiff_t(bc_index(y + 1, a.ny, per)) - y) * ptrdiff_t(row);
+        const size_t iym = i + (ptrdiff_t(bc_index(y - 1, a.ny, per)) - y) * ptrdiff_t(row);
+        const size_t izp = i + (ptrdiff_t(bc_index(z + 1, a.nz, per)) - z) * ptrdiff_t(pln);
+        const size_t izm = i + (ptrdiff_t(bc_index(z - 1, a.nz, per)) - z) * ptrdiff_t(pln);
+        float f[4], dT[4], gx[4], gy[4], gz[4], R[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float* q0 = c == 0 ? a.s_0 : a.u_0 + size_t(c - 1) * N;
+            const float* qm = c == 0 ? a.s_m : a.u_m + size_t(c - 1) * N;
+            const float* qp = c == 0 ? a.s_p : a.u_p + size_t(c - 1) * N;
+            f[c] = __ldg(q0 + i);
+            dT[c] = central_diff(__ldg(qp + i), __ldg(qm + i), a.inv2dt);
+            gx[c] = central_diff(__ldg(q0 + ixp), __ldg(q0 + ixm), a.inv2hx);
+            gy[c] = central_diff(__ldg(q0 + iyp), __ldg(q0 + iym), a.inv2hy);
+            gz[c] = central_diff(__ldg(q0 + izp), __ldg(q0 + izm), a.inv2hz);
+        }
+        point_residual(f, gx, gy, gz, dT, R);
+        const float Rs = R[0], Rx = R[1], Ry = R[2], Rz = R[3];
+        if (WRITE_R) {
+            if (a.R[0]) a.R[0][i] = SCALE ? a.scale_s * Rs : Rs;
+            if (a.R[1]) a.R[1][i] = SCALE ? a.scale_u * Rx : Rx;
+            if (a.R[2]) a.R[2][i] = SCALE ? a.scale_u * Ry : Ry;
+            if (a.R[3]) a.R[3][i] = SCALE ? a.scale_u * Rz : Rz;
+        }
+        if (REDUCE) {
+            acc_s = double(Rs) * double(Rs);
+            acc_u = double(Rx) * double(Rx) + double(Ry) * double(Ry) + double(Rz) * double(Rz);
+        }
+    }
+    if (REDUCE) grid_reduce2<8>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag);
+}
+
+// g = scale * R (reference src/phys_cpu.cpp:151-170); four arrays in one launch, float4-vectorised
+// when N % 4 == 0 (all pointers come from cudaMalloc or are at least 16-byte aligned by contract).
+struct ScaleArgs {
+    const float* R[4];
+    float* G[4];
+    float scale[4];
+    size_t n;
+};
+
+__global__ void __launch_bounds__(256) k_scale4(const ScaleArgs a, int vec4) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    const size_t t0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float s = a.scale[c];
+        if (vec4) {
+            const float4* r = reinterpret_cast<const float4*>(a.R[c]);
+            float4* g = reinterpret_cast<float4*>(a.G[c]);
+            for (size_t i = t0; i < a.n / 4; i += stride) {
+                const float4 v = __ldg(r + i);
+                g[i] = make_float4(s * v.x, s * v.y, s * v.z, s * v.w);
+            }
+        } else {
+            for (size_t i = t0; i < a.n; i += stride) a.G[c][i] = s * __ldg(a.R[c] + i);
+        }
+    }
+}
+
+}  // namespace physad

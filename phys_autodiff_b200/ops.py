@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference's operator interface over the C-ABI.
+
+Two layers, both thin:
+
+* ``Context`` -- device-resident calls (torch CUDA tensors are used only as device buffers and for
+  their stream; all arithmetic happens in libphysad_b200.so) plus the multi-GPU slab driver.
+* module-level functions with the reference's names (``mlp_grid_infer_cuda``,
+  ``mlp_generate_fields_cuda``, ``cuda_phys_residuals_fused`` ...) taking/returning host numpy
+  arrays -- the host-pointer contract of the reference API (include/phys.h:66), so parity tests
+  read like the reference's own tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import Grid, MLPConfig, PhysWeights, CSlab, check, ptr
+
+
+def slab_for_rank(nz: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous z-plane range of `rank` (z is the slowest index, so every output array of a rank
+    is one contiguous block).  Remainder planes are spread over the first ranks."""
+    return (rank * nz) // world, ((rank + 1) * nz) // world
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Context:
+    """Owns a physad_ctx: resident weights, reduction scratch and staging buffers of one GPU."""
+
+    def __init__(self, device: Optional[int] = None):
+        self._lib = capi.lib()
+        self._h = C.c_void_p()
+        check(self._lib.physad_ctx_create(C.byref(self._h), C.c_int(-1 if device is None else device)), "ctx_create")
+        self.cfg: Optional[MLPConfig] = None
+
+    def close(self):
+        if self._h:
+            self._lib.physad_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- bookkeeping -------------------------------------------------------------------------
+    @property
+    def sm_count(self) -> int:
+        return int(self._lib.physad_ctx_sm_count(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.physad_launch_count(self._h))
+
+    def set_fused_variant(self, v: int) -> int:
+        return int(self._lib.physad_set_fused_variant(self._h, C.c_int(v)))
+
+    def set_weights(self, cfg: MLPConfig, W1, b1, W2, b2) -> None:
+        W1, b1, W2, b2 = _f32(W1), _f32(b1), _f32(W2), _f32(b2)
+        assert W1.size == cfg.H * cfg.In and b1.size == cfg.H and W2.size == cfg.Out * cfg.H and b2.size == cfg.Out
+        c = cfg.c()
+        check(self._lib.physad_set_weights(self._h, C.byref(c), ptr(W1), ptr(b1), ptr(W2), ptr(b2)), "set_weights")
+        self.cfg = cfg
+
+    # -- helpers -------------------------------------------------------------------------------
+    @staticmethod
+    def _stream():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _slab(g: Grid, slab):
+        z0, z1 = (0, g.nz) if slab is None else slab
+        return CSlab(z0, z1), (z1 - z0) * g.ny * g.nx
+
+    @staticmethod
+    def _empty(n, dtype=None):
+        import torch
+        return torch.empty(n, dtype=dtype or torch.float32, device="cuda")
+
+    # -- MLP -------------------------------------------------------------------------------------
+    def mlp_forward(self, x):
+        """y[B,Out] = MLP(x[B,In]) on device tensors (mlp_forward<ExecCuda>, include/mlp.h:5-6)."""
+        B = x.shape[0]
+        y = self._empty(B * self.cfg.Out)
+        check(self._lib.physad_mlp_forward_dev(self._h, ptr(x), ptr(y), C.c_size_t(B), self._stream()), "mlp_forward")
+        return y.view(B, self.cfg.Out)
+
+    def mlp_grid_infer(self, g: Grid, t: float, slab=None):
+        cs, n = self._slab(g, slab)
+        out = self._empty(n * 4)
+        cg = g.c()
+        check(self._lib.physad_mlp_grid_infer_dev(self._h, C.byref(cg), C.byref(cs), C.c_float(t), ptr(out),
+                                                  self._stream()), "mlp_grid_infer")
+        return out.view(n, 4)
+
+    def mlp_generate_fields(self, g: Grid, t: float, dt: float, slab=None):
+        cs, n = self._slab(g, slab)
+        s = [self._empty(n) for _ in range(3)]
+        u = [self._empty(3 * n) for _ in range(3)]
+        cg = g.c()
+        check(self._lib.physad_mlp_generate_fields_dev(self._h, C.byref(cg), C.byref(cs), C.c_float(t), C.c_float(dt),
+                                                       ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(u[0]), ptr(u[1]), ptr(u[2]),
+                                                       self._stream()), "mlp_generate_fields")
+        return s[0], s[1], s[2], u[0], u[1], u[2]
+
+    # -- physics on supplied device fields -----------------------------------------------------------
+    def phys_residuals(self, g: Grid, fields: Sequence):
+        R = [self._empty(g.N) for _ in range(4)]
+        cg = g.c()
+        check(self._lib.physad_phys_residuals_dev(self._h, C.byref(cg), *[ptr(f) for f in fields], *[ptr(r) for r in R],
+                                                  self._stream()), "phys_residuals")
+        return tuple(R)
+
+    def phys_loss_acc(self, g: Grid, fields: Sequence, want_residuals: bool = False):
+        import torch
+        acc = self._empty(2, torch.float64)
+        R = [self._empty(g.N) for _ in range(4)] if want_residuals else [None] * 4
+        cg = g.c()
+        check(self._lib.physad_phys_loss_dev(self._h, C.byref(cg), *[ptr(f) for f in fields], ptr(acc),
+                                             *[ptr(r) for r in R], self._stream()), "phys_loss")
+        return (acc, tuple(R)) if want_residuals else acc
+
+    def phys_loss(self, g: Grid, pw: PhysWeights, fields: Sequence, want_residuals: bool = False):
+        out = self.phys_loss_acc(g, fields, want_residuals)
+        acc = out[0] if want_residuals else out
+        ls, lu = self.finalize(acc.cpu().numpy(), pw, g.N)
+        return (ls, lu, out[1]) if want_residuals else (ls, lu)
+
+    def phys_backward(self, g: Grid, pw: PhysWeights, R: Sequence):
+        G = [self._empty(g.N) for _ in range(4)]
+        cg, cw = g.c(), pw.c()
+        check(self._lib.physad_phys_backward_dev(self._h, C.byref(cg), C.byref(cw), *[ptr(r) for r in R],
+                                                 *[ptr(x) for x in G], self._stream()), "phys_backward")
+        return tuple(G)
+
+    def phys_backward_from_fields(self, g: Grid, pw: PhysWeights, fields: Sequence):
+        G = [self._empty(g.N) for _ in range(4)]
+        cg, cw = g.c(), pw.c()
+        check(self._lib.physad_phys_backward_from_fields_dev(self._h, C.byref(cg), C.byref(cw), *[ptr(f) for f in fields],
+                                                             *[ptr(x) for x in G], self._stream()),
+              "phys_backward_from_fields")
+        return tuple(G)
+
+    # -- the metric path --------------------------------------------------------------------------------
+    def fused_loss_acc(self, g: Grid, t: float, dt: float, slab=None, acc=None, residuals=None):
+        """Enqueue the fused kernel for a slab; returns the device tensor {sum Rs^2, sum |Ru|^2}."""
+        import torch
+        cs, _ = self._slab(g, slab)
+        if acc is None:
+            acc = self._empty(2, torch.float64)
+        R = residuals if residuals is not None else [None] * 4
+        cg = g.c()
+        check(self._lib.physad_fused_loss_dev(self._h, C.byref(cg), C.byref(cs), C.c_float(t), C.c_float(dt), ptr(acc),
+                                              *[ptr(r) for r in R], self._stream()), "fused_loss")
+        return acc
+
+    def finalize(self, acc, pw: PhysWeights, n_global: int):
+        a = (C.c_double * 2)(float(acc[0]), float(acc[1]))
+        ls, lu = C.c_float(), C.c_float()
+        cw = pw.c()
+        self._lib.physad_finalize_loss(a, C.byref(cw), C.c_size_t(n_global), C.byref(ls), C.byref(lu))
+        return np.float32(ls.value), np.float32(lu.value)
+
+    def fused_loss(self, g: Grid, pw: PhysWeights, t: float, dt: float, group=None, want_residuals: bool = False):
+        """Whole path.  With torch.distributed initialised, each rank evaluates its z-slab and one
+        all-reduce (sum, 2 doubles) combines the partial sums; residuals, if
+        requested, stay sharded."""
+        import torch
+        import torch.distributed as dist
+        world, rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_initialized() else (1, 0)
+        slab = slab_for_rank(g.nz, rank, world)
+        n = (slab[1] - slab[0]) * g.ny * g.nx
+        R = [self._empty(n) for _ in range(4)] if want_residuals else None
+        acc = self.fused_loss_acc(g, t, dt, slab=slab, residuals=R)
+        if world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        ls, lu = self.finalize(acc.cpu().numpy(), pw, g.N)
+        return (ls, lu, tuple(R)) if want_residuals else (ls, lu)
+
+    # -- host-buffer forms (the reference's contract) -----------------------------------------------------
+    def fused_loss_host(self, g: Grid, cfg: MLPConfig, W1, b1, W2, b2, pw: PhysWeights, t: float, dt: float,
+                        want_residuals: bool = False):
+        W1, b1, W2, b2 = _f32(W1), _f32(b1), _f32(W2), _f32(b2)
+        R = [np.empty(g.N, np.float32) for _ in range(4)] if want_residuals else [None] * 4
+        ls, lu = C.c_float(), C.c_float()
+        cg, cc, cw = g.c(), cfg.c(), pw.c()
+        check(self._lib.physad_fused_loss_host(self._h, C.byref(cg), C.byref(cc), ptr(W1), ptr(b1), ptr(W2), ptr(b2),
+                                               C.byref(cw), C.c_float(t), C.c_float(dt), C.byref(ls), C.byref(lu),
+                                               *[ptr(r) for r in R]), "fused_loss_host")
+        self.cfg = cfg
+        return (np.float32(ls.value), np.float32(lu.value)) + ((tuple(R),) if want_residuals else ())
+
+    def mlp_forward_host(self, x: np.ndarray) -> np.ndarray:
+        x = _f32(x)
+        B = x.size // self.cfg.In
+        y = np.empty(B * self.cfg.Out, np.float32)
+        check(self._lib.physad_mlp_forward_host(self._h, ptr(x), ptr(y), C.c_size_t(B)), "mlp_forward_host")
+        return y
+
+    def mlp_grid_infer_host(self, g: Grid, t: float) -> np.ndarray:
+        out = np.empty(g.N * 4, np.float32)
+        cg = g.c()
+        check(self._lib.physad_mlp_grid_infer_host(self._h, C.byref(cg), C.c_float(t), ptr(out)), "mlp_grid_infer_host")
+        return out
+
+    def mlp_generate_fields_host(self, g: Grid, t: float, dt: float):
+        N = g.N
+        s = [np.empty(N, np.float32) for _ in range(3)]
+        u = [np.empty(3 * N, np.float32) for _ in range(3)]
+        cg = g.c()
+        check(self._lib.physad_mlp_generate_fields_host(self._h, C.byref(cg), C.c_float(t), C.c_float(dt), ptr(s[0]),
+                                                        ptr(s[1]), ptr(s[2]), ptr(u[0]), ptr(u[1]), ptr(u[2])),
+              "mlp_generate_fields_host")
+        return s[0], s[1], s[2], u[0], u[1], u[2]
+
+    def phys_residuals_host(self, g: Grid, fields, timed: bool = False):
+        fields = [_f32(f) for f in fields]
+        R = [np.empty(g.N, np.float32) for _ in range(4)]
+        ms = C.c_float(-1.0)
+        cg = g.c()
+        check(self._lib.physad_phys_residuals_host(self._h, C.byref(cg), *[ptr(f) for f in fields], *[ptr(r) for r in R],
+                                                   C.byref(ms) if timed else None), "phys_residuals_host")
+        return (tuple(R), ms.value) if timed else tuple(R)
+
+    def phys_loss_host(self, g: Grid, pw: PhysWeights, fields, want_residuals: bool = False):
+        fields = [_f32(f) for f in fields]
+        R = [np.empty(g.N, np.float32) for _ in range(4)] if want_residuals else [None] * 4
+        ls, lu = C.c_float(), C.c_float()
+        cg, cw = g.c(), pw.c()
+        check(self._lib.physad_phys_loss_host(self._h, C.byref(cg), C.byref(cw), *[ptr(f) for f in fields], C.byref(ls),
+                                              C.byref(lu), *[ptr(r) for r in R]), "phys_loss_host")
+        return (np.float32(ls.value), np.float32(lu.value)) + ((tuple(R),) if want_residuals else ())
+
+    def phys_backward_host(self, g: Grid, pw: PhysWeights, R):
+        R = [_f32(r) for r in R]
+        G = [np.empty(g.N, np.float32) for _ in range(4)]
+        cg, cw = g.c(), pw.c()
+        check(self._lib.physad_phys_backward_host(self._h, C.byref(cg), C.byref(cw), *[ptr(r) for r in R],
+                                                  *[ptr(x) for x in G]), "phys_backward_host")
+        return tuple(G)
+
+    def phys_backward_from_fields_host(self, g: Grid, pw: PhysWeights, fields):
+        fields = [_f32(f) for f in fields]
+        G = [np.empty(g.N, np.float32) for _ in range(4)]
+        cg, cw = g.c(), pw.c()
+        check(self._lib.physad_phys_backward_from_fields_host(self._h, C.byref(cg), C.byref(cw), *[ptr(f) for f in fields],
+                                                              *[ptr(x) for x in G]), "phys_backward_from_fields_host")
+        return tuple(G)
+
+
+def mlp_random_init(H: int, seed: int = 42, scale: float = 0.5, In: int = 4, Out: int = 4):
+    """phys::mlp_random_init (reference include/mlp_grid.h:34): returns (W1, b1, W2, b2). Host only."""
+    W1 = np.empty(H * In, np.float32); b1 = np.empty(H, np.float32)
+    W2 = np.empty(Out * H, np.float32); b2 = np.empty(Out, np.float32)
+    f = capi.lib().physad_mlp_random_init
+    f.restype = None
+    f(C.c_int(In), C.c_int(H), C.c_int(Out), C.c_uint(seed), C.c_float(scale), ptr(W1), ptr(b1), ptr(W2), ptr(b2))
+    return W1, b1, W2, b2
+
+
+# ---- reference-named host functions (one shared context, like the C++ layer) -----------------------
+_CTX: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _CTX
+    if _CTX is None:
+        _CTX = Context()
+    return _CTX
+
+
+def mlp_infer_cuda(cfg: MLPConfig, w, coords: np.ndarray) -> np.ndarray:
+    c = default_context()
+    c.set_weights(cfg, *w)
+    return c.mlp_forward_host(coords)
+
+
+def mlp_grid_infer_cuda(g: Grid, cfg: MLPConfig, w, t: float) -> np.ndarray:
+    c = default_context()
+    c.set_weights(cfg, *w)
+    return c.mlp_grid_infer_host(g, t)
+
+
+def mlp_generate_fields_cuda(g: Grid, cfg: MLPConfig, w, t: float, dt: float):
+    c = default_context()
+    c.set_weights(cfg, *w)
+    return c.mlp_generate_fields_host(g, t, dt)
+
+
+def cuda_phys_residuals_fused(g: Grid, fields):
+    return default_context().phys_residuals_host(g, fields)
+
+
+cuda_phys_residuals_nonfused = cuda_phys_residuals_fused
+
+
+def cuda_phys_residuals_fused_timed(g: Grid, fields):
+    return default_context().phys_residuals_host(g, fields, timed=True)
+
+
+def cuda_phys_loss_forward_fused(g: Grid, pw: PhysWeights, fields, want_residuals: bool = False):
+    return default_context().phys_loss_host(g, pw, fields, want_residuals)
+
+
+cuda_phys_loss_forward_nonfused = cuda_phys_loss_forward_fused
+
+
+def cuda_phys_loss_backward_nonfused(g: Grid, pw: PhysWeights, R):
+    return default_context().phys_backward_host(g, pw, R)
+
+
+def cuda_phys_loss_backward_fused(g: Grid, pw: PhysWeights, fields):
+    return default_context().phys_backward_from_fields_host(g, pw, fields)
+
+
+def mlp_phys_loss_fused_cuda(g: Grid, cfg: MLPConfig, w, pw: PhysWeights, t: float, dt: float, want_residuals: bool = False):
+    return default_context().fused_loss_host(g, cfg, *w, pw, t, dt, want_residuals)

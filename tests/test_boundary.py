@@ -1,0 +1,134 @@
+"""CPU tier: the drop-in boundary.  The C-ABI library loads without a GPU, exports every symbol
+include/physad_b200.h declares (and the reference's C++ symbols), reports
+errors instead of computing on the CPU, and the product never touches oracle/."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "physad_b200.h")
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from phys_autodiff_b200 import capi
+    p = capi.library_path()
+    if not os.path.exists(p):
+        capi.build_library()
+    return p
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(physad_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(libpath):
+    from phys_autodiff_b200 import capi
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    assert sorted(capi.EXPORTS) == declared, "capi.EXPORTS out of sync with include/physad_b200.h"
+    lib = C.CDLL(libpath)
+    for s in declared:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert lib.physad_abi_version() == 1
+
+
+def test_reference_cxx_symbols_exported(libpath):
+    """Itanium-mangled names a replacement CUDA backend must define."""
+    out = subprocess.run(["nm", "-D", "--defined-only", libpath], capture_output=True, text=True, check=True).stdout
+    need = [
+        "_Z11mlp_forwardI8ExecCudaEvPKfS2_S2_S2_S2_Pfmmmm",
+        "_Z12mlp_backwardI8ExecCudaEvPKfS2_S2_S2_S2_S2_PfS3_S3_S3_mmmm",
+        "cuda_phys_residuals_nonfusedE", "cuda_phys_residuals_nonfused_timedE", "cuda_phys_loss_forward_nonfusedE",
+        "cuda_phys_loss_backward_nonfusedE", "cuda_phys_residuals_fusedE", "cuda_phys_residuals_fused_timedE",
+        "cuda_phys_loss_backward_fusedE", "mlp_infer_cudaE", "mlp_grid_infer_cudaE", "mlp_generate_fields_cudaE",
+        "mlp_random_initE", "make_grid_coordsE", "cuda_phys_loss_forward_fusedE", "mlp_phys_loss_fused_cudaE",
+    ]
+    for n in need:
+        assert n in out, n
+
+
+def test_no_cpu_fallback_without_device(libpath):
+    """Here (no GPU) context creation must fail with a CUDA status, not fall back to anything."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = C.CDLL(libpath)
+    lib.physad_last_error.restype = C.c_char_p
+    h = C.c_void_p()
+    rc = lib.physad_ctx_create(C.byref(h), C.c_int(-1))
+    assert rc != 0 and not h.value
+    assert len(lib.physad_last_error()) > 0
+
+
+def test_host_weight_init_matches_reference_stream(libpath, golden):
+    """physad_mlp_random_init is host-only code, so it can be pinned on the CPU tier."""
+    import numpy as np
+    from phys_autodiff_b200 import ops
+    arr, meta = golden
+    for c in meta["cases"]:
+        if c["kind"] == "weights":
+            w = ops.mlp_random_init(c["H"], c["seed"], c["scale"])
+            for name, a in zip(["W1", "b1", "W2", "b2"], w):
+                assert np.array_equal(a, arr[f"{c['key']}_{name}"])
+
+
+def test_finalize_loss_is_reference_formula(libpath):
+    """L = float(w * acc * (1.0/N)) (reference src/phys_cpu.cpp:146-148); pure host arithmetic."""
+    import numpy as np
+    lib = C.CDLL(libpath)
+    lib.physad_finalize_loss.restype = None
+
+    class W(C.Structure):
+        _fields_ = [("a", C.c_float), ("b", C.c_float)]
+    acc = (C.c_double * 2)(2670.937891475786, 7551.66)
+    ls, lu = C.c_float(), C.c_float()
+    lib.physad_finalize_loss(acc, C.byref(W(1.7, 0.9)), C.c_size_t(262144), C.byref(ls), C.byref(lu))
+    assert ls.value == float(np.float32(np.float64(np.float32(1.7)) * 2670.937891475786 * (1.0 / 262144)))
+    assert lu.value == float(np.float32(np.float64(np.float32(0.9)) * 7551.66 * (1.0 / 262144)))
+
+
+def test_product_never_uses_the_oracle():
+    """Only tests/, smoke() and bench.py's cpu_baseline/reference legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "phys_autodiff_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                for bad in ("import oracle", "from oracle", "liboracle", "libphysref", "oracle/"):
+                    assert bad not in txt, (f, bad)
+    out = subprocess.run(["ldd", os.path.join(pkg, "libphysad_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "physref" not in out
+
+
+def test_strict_kernels_have_no_contracted_fma_in_mlp(libpath):
+    """SASS check: the MLP grid kernel (pure MLP, no stencil) must contain FMUL/FADD and no FFMA
+    (FFMA contraction breaks residual parity)."""
+    r = subprocess.run(["cuobjdump", "-sass", libpath], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    cur, counts = None, {}
+    for line in r.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            counts[cur] = {"FFMA": 0, "FMUL": 0, "FADD": 0, "FFMA2": 0}
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            op = m.group(1)
+            if op in counts[cur]:
+                counts[cur][op] += 1
+    grid = {k: v for k, v in counts.items() if "k_mlp_grid" in k or "k_mlp_forward_4x4" in k or "k_mlp_generic" in k}
+    assert grid, "MLP kernels not found in SASS"
+    for k, v in grid.items():
+        assert v["FMUL"] > 0 and v["FADD"] > 0, (k, v)
+        # the only FFMAs allowed are the Newton steps of the three IEEE coordinate divisions
+        # (__fdiv_rn, 9 each) in the grid kernels; a contracted MLP loop would add one per MAC
+        limit = 27 if "k_mlp_grid" in k else 0
+        assert v["FFMA"] <= limit and v["FFMA2"] == 0, (k, v)

@@ -1,0 +1,147 @@
+"""CPU tier: pin the oracle.  (a) the plain-C port against the golden vectors generated from the
+unmodified reference, (b) the port against the reference library itself where it is present,
+(c) the reference's own known-answer test (test/test_phys_cpu_ref.cpp) restated on the oracle."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import bits_equal, manufactured_fields, max_rel_to_max, rel_l2
+from oracle import Grid
+
+
+def _case_grid(c):
+    return Grid(*c["g"], *c["h"], c["dt"], c["periodic"])
+
+
+def test_weights_match_golden(port, golden):
+    arr, meta = golden
+    for c in meta["cases"]:
+        if c["kind"] != "weights":
+            continue
+        w = port.mlp_random_init(c["H"], c["seed"], c["scale"])
+        for name, a in zip(["W1", "b1", "W2", "b2"], w):
+            assert np.array_equal(a, arr[f"{c['key']}_{name}"]), (c, name)
+    assert float(port.mlp_random_init(64, 777, 0.25)[0][0]) == float(np.float32(-0.173668131))
+
+
+def test_full_path_matches_golden(port, golden):
+    arr, meta = golden
+    for c in meta["cases"]:
+        if c["kind"] != "path":
+            continue
+        g = _case_grid(c)
+        n = c["name"]
+        w = port.mlp_random_init(c["H"], c["seed"], c["scale"])
+        assert bits_equal(port.mlp_grid_infer(g, w, c["t"], c["m1p1"]), arr[n + "_y"]), n
+        f = port.generate_fields(g, w, c["t"], c["dt"], c["m1p1"])
+        for k, a in zip(["sm", "s0", "sp", "um", "u0", "up"], f):
+            assert bits_equal(a, arr[f"{n}_{k}"]), (n, k)
+        ls, lu, R = port.phys_loss_forward(g, c["w"][0], c["w"][1], f, want_residuals=True)
+        for k, a in zip(["Rs", "Rx", "Ry", "Rz"], R):
+            assert bits_equal(a, arr[f"{n}_{k}"]), (n, k)
+        assert float(ls) == float(c["loss_sigma"]) and float(lu) == float(c["loss_u"]), n
+        G = port.phys_loss_backward(g, c["w"][0], c["w"][1], R)
+        for k, a in zip(["gs", "gx", "gy", "gz"], G):
+            assert bits_equal(a, arr[f"{n}_{k}"]), (n, k)
+        # composed entry point == staged calls
+        fl = port.fused_loss(g, w, c["t"], c["dt"], c["w"][0], c["w"][1], c["m1p1"], want_residuals=True)
+        assert float(fl["loss_sigma"]) == float(ls) and float(fl["loss_u"]) == float(lu)
+
+
+def test_anchor_losses_64cubed(port, golden):
+    """Scalar anchors at a BASELINE size (also listed in SURVEY.md section 7 / BASELINE.md section 2)."""
+    _, meta = golden
+    a = meta["anchors"]["64c_h32"]
+    g = Grid(64, 64, 64, 1, 1, 1, 2e-3, True)
+    w = port.mlp_random_init(32, 777, 0.25)
+    r = port.fused_loss(g, w, 0.25, 2e-3, want_residuals=True)
+    assert float(r["loss_sigma"]) == float(a["loss_sigma"]) == float(np.float32(0.00194079021))
+    assert float(r["loss_u"]) == float(a["loss_u"]) == float(np.float32(0.0100833438))
+    assert float(r["R"][0][0]) == float(a["R_sigma0"])
+
+
+def test_port_equals_reference_library(port, ref):
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    rng = np.random.default_rng(0)
+    for seed in (0, 1, 7, 2**32 - 1):
+        for H in (8, 64, 100):
+            a, b = port.mlp_random_init(H, seed, 0.3), ref.mlp_random_init(H, seed, 0.3)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    for (nx, ny, nz, per, m1p1) in [(17, 9, 5, True, True), (8, 8, 8, False, False), (3, 1, 2, True, True)]:
+        g = Grid(nx, ny, nz, 0.7, 1.3, 0.9, 3e-3, per)
+        w = ref.mlp_random_init(24, 5, 0.4)
+        assert bits_equal(port.make_grid_coords(g, 0.1, m1p1), ref.make_grid_coords(g, 0.1, m1p1))
+        fp, fr = port.generate_fields(g, w, 0.1, 3e-3, m1p1), ref.generate_fields(g, w, 0.1, 3e-3, m1p1)
+        assert all(bits_equal(x, y) for x, y in zip(fp, fr))
+        # random (non-MLP) fields through the physics
+        f = [rng.standard_normal(g.N).astype(np.float32) for _ in range(3)] + \
+            [rng.standard_normal(3 * g.N).astype(np.float32) for _ in range(3)]
+        rp, rr = port.phys_loss_forward(g, 1.1, 0.8, f, True), ref.phys_loss_forward(g, 1.1, 0.8, f, True)
+        assert float(rp[0]) == float(rr[0]) and float(rp[1]) == float(rr[1])
+        assert all(bits_equal(x, y) for x, y in zip(rp[2], rr[2]))
+    # generic dims through mlp_forward
+    B, In, H, Out = 37, 5, 19, 3
+    x = rng.standard_normal(B * In).astype(np.float32)
+    W1 = rng.standard_normal(H * In).astype(np.float32); b1 = rng.standard_normal(H).astype(np.float32)
+    W2 = rng.standard_normal(Out * H).astype(np.float32); b2 = rng.standard_normal(Out).astype(np.float32)
+    assert bits_equal(port.mlp_forward(x, W1, b1, W2, b2, B, In, H, Out), ref.mlp_forward(x, W1, b1, W2, b2, B, In, H, Out))
+
+
+def test_reference_mt_driver_is_bit_identical(ref):
+    """The threaded chunk driver in oracle/ref_shim.cpp must equal the reference's one-call path."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    g = Grid(20, 12, 9, 1, 1, 1, 2e-3, True)
+    w = ref.mlp_random_init(32, 777, 0.25)
+    f = ref.generate_fields(g, w, 0.25, 2e-3)
+    ls, lu, R = ref.phys_loss_forward(g, 1.0, 1.0, f, True)
+    r = ref.fused_loss(g, w, 0.25, 2e-3, threads=3, want_residuals=True)
+    assert float(r["loss_sigma"]) == float(ls) and float(r["loss_u"]) == float(lu)
+    assert all(bits_equal(a, b) for a, b in zip(r["R"], R))
+
+
+def test_known_answer_manufactured_solution(checker):
+    """test/test_phys_cpu_ref.cpp: sigma = sin(x+y+z-t), u = (1,1,1) on 64x64x32 =>
+    R_sigma = cos(phi) * (-sin(dt)/dt + sum_d sin(h_d)/h_d), R_u = 0; then g = 2 w / N * R."""
+    nx, ny, nz = 64, 64, 32
+    g = Grid(nx, ny, nz, 2 * math.pi / nx, 2 * math.pi / ny, 2 * math.pi / nz, 1e-3, True)
+    t = 1.2345
+    f = manufactured_fields(g, t)
+    Rs, Rx, Ry, Rz = checker.phys_residuals(g, f)
+    x = (np.arange(nx) * g.hx)[None, None, :]; y = (np.arange(ny) * g.hy)[None, :, None]; z = (np.arange(nz) * g.hz)[:, None, None]
+    phi = x + y + z - t
+    coef = -math.sin(g.dt) / g.dt + math.sin(g.hx) / g.hx + math.sin(g.hy) / g.hy + math.sin(g.hz) / g.hz
+    exact = (np.cos(phi) * coef).reshape(-1)
+    assert rel_l2(Rs, exact) <= 3e-4 and np.max(np.abs(Rs - exact)) <= 1e-3        # :87
+    assert max(np.max(np.abs(Rx)), np.max(np.abs(Ry)), np.max(np.abs(Rz))) <= 1e-6  # :76
+    G = checker.phys_loss_backward(g, 1.7, 0.9, (Rs, Rx, Ry, Rz))
+    want = (np.float32(2.0) * np.float32(1.7) / np.float32(g.N)) * Rs
+    assert rel_l2(G[0], want) <= 1e-7 and np.max(np.abs(G[0] - want)) <= 1e-6         # :120
+
+
+def test_reference_own_test_binary_passes():
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "test_phys_cpu_ref")
+    if not os.path.exists(exe):
+        pytest.skip("reference test binary not built here")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "[PASS]" in r.stdout, r.stdout + r.stderr
+
+
+def test_edge_cases_on_oracle(port):
+    """Degenerate extents: n=1 axes give coordinate 0 and zero differences; clamp halves edges."""
+    g = Grid(1, 1, 1, 1, 1, 1, 2e-3, True)
+    w = port.mlp_random_init(16, 42, 0.5)
+    r = port.fused_loss(g, w, 0.25, 2e-3, want_residuals=True)
+    f = port.generate_fields(g, w, 0.25, 2e-3)
+    dts = (np.float64(f[2][0]) - np.float64(f[0][0])) * (1.0 / (2.0 * np.float64(np.float32(2e-3))))
+    assert float(r["R"][0][0]) == float(np.float32(dts))  # all spatial terms vanish
+    # clamp: a field linear in x has interior slope a, edge slope a/2 (divisor stays 2h)
+    g = Grid(6, 1, 1, 1, 1, 1, 1.0, False)
+    s = np.arange(6, dtype=np.float32) * 2
+    u = np.concatenate([np.ones(6, np.float32), np.zeros(12, np.float32)])
+    Rs, *_ = port.phys_residuals(g, (s, s, s, u, u, u))
+    assert list(Rs) == [1.0, 2.0, 2.0, 2.0, 2.0, 1.0]
