@@ -107,7 +107,7 @@ void fill_const(const physad_ctx* c, const float tcoord[3], MlpConst<H>& k) {
             // them into anything wider)
             volatile float pm = w[3] * tcoord[0], p0 = w[3] * tcoord[1], pp = w[3] * tcoord[2];
             k.lt[h] = make_float4(pm, p0, pp, 0.f);
-            k.w2[h] = make_float4(c->W2[h], c->W2[size_t(h_rt) + h], c->W2[2 * size_t(h_rt) + h], c->W2[3 * size_t(h_rt) + h]);
+            k.w2[h] = make_float4(c->W2[size_t(h_rt) + h], c->W2[h], c->W2[3 * size_t(h_rt) + h], c->W2[2 * size_t(h_rt) + h]);
         } else {
             k.l1[h] = k.lt[h] = k.w2[h] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -132,11 +132,11 @@ struct FusedGeom {
     size_t smem;
 };
 
-template <int H, int P, int TYB, int UNROLL, int MINB>
+template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED>
 int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], float dt, double* acc,
                    float* const R[4], cudaStream_t st) {
     constexpr int TX = 32, TY = TYB * P;
-    auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB>;
+    auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB, PACKED>;
     const size_t smem = size_t(4) * 4 * (TX + 2) * (TY + 2) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
@@ -148,28 +148,17 @@ int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
     if (per_sm < 1) return fail(PHYSAD_E_UNSUPPORTED, "fused kernel does not fit on an SM");
     const int tiles_x = (g->nx + TX - 1) / TX, tiles_y = (g->ny + TY - 1) / TY;
     const int tiles = tiles_x * tiles_y, nzl = s.z_end - s.z_begin;
-    const long long slots = (long long)per_sm * c->sm_count;
-    // z chunks: minimise waves * (planes per chunk + cost of the two time-t-only halo planes)
-    int best_nc = 1;
-    if (const char* e = getenv("PHYSAD_NCHUNKS")) {
-        best_nc = std::max(1, std::min(nzl, atoi(e)));
-    } else {
-        double best = 1e300;
-        for (int nc = 1; nc <= nzl; ++nc) {
-            const long long blocks = (long long)tiles * nc;
-            const double waves = double((blocks + slots - 1) / slots);
-            const double cost = waves * (double((nzl + nc - 1) / nc) + 0.75);
-            if (cost < best * 0.999) { best = cost; best_nc = nc; }
-        }
-    }
+    // persistent grid: one block per resident slot, each owning an equal share of the tile-planes
+    const long long slots = (long long)per_sm * c->sm_count, work = (long long)tiles * nzl;
+    long long blocks = std::min(slots, work);
+    if (const char* e = getenv("PHYSAD_FUSED_BLOCKS")) blocks = std::max(1LL, std::min(work, atoll(e)));
     FusedArgs a{};
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
     a.z_begin = s.z_begin; a.z_end = s.z_end;
-    a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.nchunks = best_nc;
+    a.tiles_x = tiles_x; a.tiles_y = tiles_y;
     a.m1p1 = c->cfg.norm == 1; a.periodic = g->periodic != 0;
     a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
-    const size_t blocks = size_t(tiles) * best_nc;
-    if (int rc = ensure_partials(c, blocks)) return rc;
+    if (int rc = ensure_partials(c, size_t(blocks))) return rc;
     a.partials = c->partials; a.ticket = c->ticket; a.acc_out = acc;
     for (int k = 0; k < 4; ++k) a.R[k] = R[k];
     MlpConst<H> k;
@@ -186,12 +175,18 @@ int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
                    float* const R[4], cudaStream_t st) {
     switch (c->fused_variant) {
         default:
-        case 0: return launch_fused_t<H, 2, 8, 4, 2>(c, g, s, tc, dt, acc, R, st);
-        case 1: return launch_fused_t<H, 1, 16, 4, 2>(c, g, s, tc, dt, acc, R, st);
-        case 2: return launch_fused_t<H, 2, 16, 4, 1>(c, g, s, tc, dt, acc, R, st);
-        case 3: return launch_fused_t<H, 4, 8, 2, 1>(c, g, s, tc, dt, acc, R, st);
-        case 4: return launch_fused_t<H, 2, 8, 8, 2>(c, g, s, tc, dt, acc, R, st);
-        case 5: return launch_fused_t<H, 1, 8, 4, 4>(c, g, s, tc, dt, acc, R, st);
+        case 0: return launch_fused_t<H, 4, 8, 2, 1, true>(c, g, s, tc, dt, acc, R, st);
+        case 1: return launch_fused_t<H, 2, 8, 4, 2, true>(c, g, s, tc, dt, acc, R, st);
+        case 2: return launch_fused_t<H, 2, 16, 4, 1, true>(c, g, s, tc, dt, acc, R, st);
+        case 3: return launch_fused_t<H, 4, 8, 2, 1, false>(c, g, s, tc, dt, acc, R, st);   // scalar layer 2 (round-1 first cut)
+        case 4: return launch_fused_t<H, 4, 8, 4, 1, true>(c, g, s, tc, dt, acc, R, st);
+        case 5: return launch_fused_t<H, 1, 8, 4, 4, true>(c, g, s, tc, dt, acc, R, st);
+        case 6: return launch_fused_t<H, 2, 8, 2, 3, true>(c, g, s, tc, dt, acc, R, st);
+        case 7: return launch_fused_t<H, 4, 4, 2, 2, true>(c, g, s, tc, dt, acc, R, st);
+        case 8: return launch_fused_t<H, 4, 8, 2, 2, true>(c, g, s, tc, dt, acc, R, st);
+        case 9: return launch_fused_t<H, 4, 16, 2, 1, true>(c, g, s, tc, dt, acc, R, st);
+        case 10: return launch_fused_t<H, 3, 8, 2, 2, true>(c, g, s, tc, dt, acc, R, st);
+        case 11: return launch_fused_t<H, 4, 8, 1, 2, true>(c, g, s, tc, dt, acc, R, st);
     }
 }
 

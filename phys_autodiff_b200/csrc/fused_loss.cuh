@@ -2,7 +2,11 @@
 // reduction for a z-slab of the grid, one launch, nothing but 16 bytes leaves the chip.
 //
 // Work decomposition
-//   block  = one (TX x TY) tile of (x,y) columns x one chunk of z planes; it MARCHES along z.
+//   work   = tiles x planes "tile-planes", linearised tile-major.  The grid is PERSISTENT: one block per
+//            resident slot (SMs x blocks/SM), block b owns the contiguous range [b W/G, (b+1) W/G) of
+//            tile-planes, i.e. at most two z-segments of (usually) two different tiles -- every block
+//            gets the same number of planes (+-1), so there is no partial last wave.
+//   block  = marches along z over each of its segments of one (TX x TY) tile of (x,y) columns.
 //   thread = P columns that share x (rows ty, ty+TYB, ...); 32 lanes of a warp = 32 consecutive x.
 //   step k = plane zk = chunk_begin - 1 + k.  Interior steps evaluate all three time slices for
 //            the thread's columns (sharing the layer-1 prefix, see mlp_eval.cuh); the first and the
@@ -29,7 +33,7 @@ namespace physad {
 struct FusedArgs {
     int nx, ny, nz;          // global grid
     int z_begin, z_end;      // slab [z_begin, z_end)
-    int tiles_x, tiles_y, nchunks;
+    int tiles_x, tiles_y;    // tile grid; work = tiles_x*tiles_y*(z_end-z_begin) tile-planes over gridDim.x blocks
     int m1p1, periodic;
     float inv2dt, inv2hx, inv2hy, inv2hz;
     double2* partials;       // [gridDim.x]
@@ -85,7 +89,7 @@ __device__ __forceinline__ void grid_reduce2(double a, double b, double2* partia
     }
 }
 
-template <int H, int P, int TYB, int UNROLL, int MINB>
+template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED>
 __global__ void __launch_bounds__(32 * TYB, MINB)
 k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) {
     constexpr int TX = 32, TY = TYB * P, NWARPS = TYB;
@@ -99,15 +103,20 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // warp id == ty
     const bool m1p1 = a.m1p1 != 0, per = a.periodic != 0;
 
-    int b = blockIdx.x;
-    const int tile_x = b % a.tiles_x; b /= a.tiles_x;
-    const int tile_y = b % a.tiles_y; b /= a.tiles_y;
-    const int chunk = b;
     const int nzl = a.z_end - a.z_begin;
-    const int zc0 = a.z_begin + int((long long)chunk * nzl / a.nchunks);
-    const int zc1 = a.z_begin + int((long long)(chunk + 1) * nzl / a.nchunks);
-    const int nplanes = zc1 - zc0;
-    const int x0 = tile_x * TX, y0 = tile_y * TY;
+    const long long W = (long long)a.tiles_x * a.tiles_y * nzl;
+    const long long w_end = W * (blockIdx.x + 1) / gridDim.x;
+    long long wpos = W * blockIdx.x / gridDim.x;
+    double acc_s = 0.0, acc_u = 0.0;
+    int kbuf = 0;  // running plane-buffer index (keeps rotating across segments)
+
+  while (wpos < w_end) {
+    const int tile = int(wpos / nzl);
+    const int zs = int(wpos - (long long)tile * nzl);
+    const int nplanes = int(w_end - wpos < (long long)(nzl - zs) ? w_end - wpos : (long long)(nzl - zs));
+    wpos += nplanes;
+    const int zc0 = a.z_begin + zs;
+    const int x0 = (tile % a.tiles_x) * TX, y0 = (tile / a.tiles_x) * TY;
 
     // this thread's columns
     const int gx = x0 + tx;
@@ -142,17 +151,16 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
     for (int j = 0; j < P; ++j)
 #pragma unroll
         for (int c = 0; c < 4; ++c) dT[j][c] = 0.f;
-    double acc_s = 0.0, acc_u = 0.0;
 
-    for (int k = 0; k <= nplanes + 1; ++k) {
+    for (int k = 0; k <= nplanes + 1; ++k, ++kbuf) {
         const int zk = zc0 - 1 + k;
         const float cz = axis_coord(bc_index(zk, a.nz, per), a.nz, m1p1);
-        float* pl = buf + (k & (NB - 1)) * PLANE;
+        float* pl = buf + (kbuf & (NB - 1)) * PLANE;
         const bool halo_plane = (k == 0) || (k == nplanes + 1);
         float dTn[P][4];
         if (halo_plane) {
             float y[P][1][4];
-            mlp_eval<H, 1, P, UNROLL>(w, cx, cy, cz, y);
+            mlp_eval<H, 1, P, UNROLL, PACKED>(w, cx, cy, cz, y);
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 const int o = (1 + ty + j * TYB) * SX + 1 + tx;
@@ -161,7 +169,7 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
             }
         } else {
             float y[P][3][4];
-            mlp_eval<H, 3, P, UNROLL>(w, cx, cy, cz, y);
+            mlp_eval<H, 3, P, UNROLL, PACKED>(w, cx, cy, cz, y);
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 const int o = (1 + ty + j * TYB) * SX + 1 + tx;
@@ -174,10 +182,10 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
             // ring duty for this plane (x/y neighbours of the tile edge), rotating over warps
 #pragma unroll
             for (int i = 0; i < NTASK; ++i) {
-                if ((i + k) % NWARPS == ty) {
+                if ((i + kbuf) % NWARPS == ty) {
                     float yr[1][1][4];
                     const float rc[1] = {rcy[i]};
-                    mlp_eval<H, 1, 1, UNROLL>(w, rcx[i], rc, cz, yr);
+                    mlp_eval<H, 1, 1, UNROLL, PACKED>(w, rcx[i], rc, cz, yr);
                     if (roff[i] >= 0) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) pl[c * CH + roff[i]] = yr[0][0][c];
@@ -188,8 +196,8 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
         __syncthreads();
         if (k >= 2) {
             // residual of plane zk-1: centre/x/y neighbours from plane buffer k-1, z neighbours from k-2 and k
-            const float* pc = buf + ((k - 1) & (NB - 1)) * PLANE;
-            const float* pm = buf + ((k - 2) & (NB - 1)) * PLANE;
+            const float* pc = buf + ((kbuf - 1) & (NB - 1)) * PLANE;
+            const float* pm = buf + ((kbuf - 2) & (NB - 1)) * PLANE;
             const float* pp = pl;
             const int zl = zk - 1 - a.z_begin;  // slab-local plane of the residual
 #pragma unroll
@@ -221,6 +229,9 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
 #pragma unroll
             for (int c = 0; c < 4; ++c) dT[j][c] = dTn[j][c];
     }
+    // The next segment starts writing plane buffers that the slowest warp may still be reading.
+    __syncthreads();
+  }
     grid_reduce2<NWARPS>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag);
 }
 

@@ -26,7 +26,7 @@ template <int H>
 struct MlpConst {
     float4 l1[H];  // {b1[h], W1[h,0], W1[h,1], W1[h,2]}
     float4 lt[H];  // {W1[h,3]*t_minus, W1[h,3]*t_0, W1[h,3]*t_plus, 0}   (rounded fp32 products)
-    float4 w2[H];  // {W2[0,h], W2[1,h], W2[2,h], W2[3,h]}
+    float4 w2[H];  // {W2[1,h], W2[0,h], W2[3,h], W2[2,h]}  (output pairs stored half-swapped, see mlp_eval)
     float4 b2;     // {b2[0..3]}
 };
 
@@ -52,25 +52,69 @@ __device__ __forceinline__ int bc_index(int v, int n, bool periodic) {
     return v < 0 ? 0 : (v > n - 1 ? n - 1 : v);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100a FMUL2 / FADD2) ------------------------------------------
+// The FP32 pipe retires 128 lane-ops/clk/SM whether they are issued as scalar or as packed f32x2
+// instructions (profiles/r01_microbench_fp32_*.json: strict 36.9 TFLOP/s == strict2 37.1), but a packed
+// instruction takes ONE issue slot for two lane-ops.  The scalar kernel is issue-bound (ncu: 95 % issue
+// utilisation at 78 % FMA-pipe utilisation), so layer 2 -- 24 of the ~31 pipe ops per point and hidden
+// unit -- is issued packed: the two halves are two OUTPUTS (y0,y1 | y2,y3) sharing one activation, which
+// the hardware broadcasts from a single register (SASS operand `R.F32`), and the weight pair comes
+// straight from a 64-bit uniform load.  Each half is still a separately rounded multiply followed by a
+// separately rounded add in the reference's h order, so results stay bit-identical.
+// ptxas would contract mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 (single rounding -- measured, even
+// with .rn and -fmad=false) when the product has one use; feeding the product half-swapped (a free
+// `.LO_HI` operand swizzle in SASS) prevents that, so weight pairs are stored swapped.
+// tests/test_boundary.py asserts the kernels contain no FFMA2.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 mul2_rn(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// acc + swap_halves(p), each half rounded to nearest
+__device__ __forceinline__ f32x2 add2_rn_swapped(f32x2 acc, f32x2 p) {
+    float lo, hi;
+    unpack2(p, lo, hi);
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(acc), "l"(pack2(hi, lo)));
+    return r;
+}
+
 // NS = 3: all three time slices (y[j][0|1|2] = t-dt | t | t+dt);  NS = 1: time t only (y[j][0]).
-// P points share cx and cz and differ in cy.
-template <int H, int NS, int P, int UNROLL>
+// P points share cx and cz and differ in cy.  PACKED selects the FMUL2/FADD2 layer 2.
+template <int H, int NS, int P, int UNROLL, bool PACKED>
 __device__ __forceinline__ void mlp_eval(const MlpConst<H>& w, float cx, const float (&cy)[P], float cz,
                                          float (&y)[P][NS][4]) {
     const float4 b2 = w.b2;
+    f32x2 q01[P][NS], q23[P][NS];  // packed accumulators {y0,y1}, {y2,y3}
 #pragma unroll
     for (int j = 0; j < P; ++j)
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-            y[j][s][0] = b2.x; y[j][s][1] = b2.y; y[j][s][2] = b2.z; y[j][s][3] = b2.w;
+            if (PACKED) {
+                q01[j][s] = pack2(b2.x, b2.y);
+                q23[j][s] = pack2(b2.z, b2.w);
+            } else {
+                y[j][s][0] = b2.x; y[j][s][1] = b2.y; y[j][s][2] = b2.z; y[j][s][3] = b2.w;
+            }
         }
 #pragma unroll UNROLL
     for (int h = 0; h < H; ++h) {
         const float4 a = w.l1[h];
         const float4 tt = w.lt[h];
-        const float4 c = w.w2[h];
+        const float4 c = w.w2[h];  // {W2[1,h], W2[0,h], W2[3,h], W2[2,h]}: pairs stored swapped
         const float sx = __fadd_rn(a.x, __fmul_rn(a.y, cx));  // b1 + W1[h,0]*x
         const float mz = __fmul_rn(a.w, cz);                  // W1[h,2]*z
+        const f32x2 c10 = pack2(c.x, c.y), c32 = pack2(c.z, c.w);
 #pragma unroll
         for (int j = 0; j < P; ++j) {
             const float sxyz = __fadd_rn(__fadd_rn(sx, __fmul_rn(a.z, cy[j])), mz);
@@ -78,12 +122,27 @@ __device__ __forceinline__ void mlp_eval(const MlpConst<H>& w, float cx, const f
             for (int s = 0; s < NS; ++s) {
                 const float pt = (NS == 1) ? tt.y : (s == 0 ? tt.x : (s == 1 ? tt.y : tt.z));
                 const float act = relu_ref(__fadd_rn(sxyz, pt));
-                y[j][s][0] = __fadd_rn(y[j][s][0], __fmul_rn(c.x, act));
-                y[j][s][1] = __fadd_rn(y[j][s][1], __fmul_rn(c.y, act));
-                y[j][s][2] = __fadd_rn(y[j][s][2], __fmul_rn(c.z, act));
-                y[j][s][3] = __fadd_rn(y[j][s][3], __fmul_rn(c.w, act));
+                if (PACKED) {
+                    const f32x2 aa = pack2(act, act);
+                    q01[j][s] = add2_rn_swapped(q01[j][s], mul2_rn(aa, c10));
+                    q23[j][s] = add2_rn_swapped(q23[j][s], mul2_rn(aa, c32));
+                } else {
+                    y[j][s][0] = __fadd_rn(y[j][s][0], __fmul_rn(c.y, act));
+                    y[j][s][1] = __fadd_rn(y[j][s][1], __fmul_rn(c.x, act));
+                    y[j][s][2] = __fadd_rn(y[j][s][2], __fmul_rn(c.w, act));
+                    y[j][s][3] = __fadd_rn(y[j][s][3], __fmul_rn(c.z, act));
+                }
             }
         }
+    }
+    if (PACKED) {
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                unpack2(q01[j][s], y[j][s][0], y[j][s][1]);
+                unpack2(q23[j][s], y[j][s][2], y[j][s][3]);
+            }
     }
 }
 

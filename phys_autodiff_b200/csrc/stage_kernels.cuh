@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_mlp_grid(const __grid_constant__ MlpCon
     const float cz = axis_coord(z, a.nz, m1p1);
     if (FIELDS) {
         float o[1][3][4];
-        mlp_eval<H, 3, 1, UNROLL>(w, cx, cy, cz, o);
+        mlp_eval<H, 3, 1, UNROLL, true>(w, cx, cy, cz, o);
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
             a.sigma[s][i] = o[0][s][0];
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_mlp_grid(const __grid_constant__ MlpCon
         }
     } else {
         float o[1][1][4];
-        mlp_eval<H, 1, 1, UNROLL>(w, cx, cy, cz, o);
+        mlp_eval<H, 1, 1, UNROLL, true>(w, cx, cy, cz, o);
         a.out_aos[i] = make_float4(o[0][0][0], o[0][0][1], o[0][0][2], o[0][0][3]);
     }
 }

@@ -117,17 +117,22 @@ def test_strict_kernels_have_no_contracted_fma_in_mlp(libpath):
         m = re.search(r"Function : (\S+)", line)
         if m:
             cur = m.group(1)
-            counts[cur] = {"FFMA": 0, "FMUL": 0, "FADD": 0, "FFMA2": 0}
+            counts[cur] = {"FFMA": 0, "FMUL": 0, "FADD": 0, "FFMA2": 0, "FMUL2": 0, "FADD2": 0}
             continue
         m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
         if m and cur:
             op = m.group(1)
             if op in counts[cur]:
                 counts[cur][op] += 1
+    # packed layer 2: FMUL2 and FADD2 must stay separate instructions in every kernel that has them
+    assert all(v["FFMA2"] == 0 for v in counts.values()), {k: v for k, v in counts.items() if v["FFMA2"]}
+    fused = {k: v for k, v in counts.items() if "k_fused_mlp_phys_loss" in k}
+    assert fused and all(v["FMUL"] + v.get("FMUL2", 0) > 0 for v in fused.values())
     grid = {k: v for k, v in counts.items() if "k_mlp_grid" in k or "k_mlp_forward_4x4" in k or "k_mlp_generic" in k}
     assert grid, "MLP kernels not found in SASS"
     for k, v in grid.items():
-        assert v["FMUL"] > 0 and v["FADD"] > 0, (k, v)
+        assert v["FMUL"] + v["FMUL2"] > 0 and v["FADD"] + v["FADD2"] > 0, (k, v)
+        assert v["FMUL2"] == v["FADD2"], (k, v)
         # the only FFMAs allowed are the Newton steps of the three IEEE coordinate divisions
         # (__fdiv_rn, 9 each) in the grid kernels; a contracted MLP loop would add one per MAC
         limit = 27 if "k_mlp_grid" in k else 0
