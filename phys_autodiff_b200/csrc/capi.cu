@@ -99,19 +99,22 @@ int template_h(int H) { return H <= 32 ? 32 : (H <= 64 ? 64 : (H <= 128 ? 128 : 
 template <int H>
 void fill_const(const physad_ctx* c, const float tcoord[3], MlpConst<H>& k) {
     const int h_rt = c->cfg.H;
-    for (int h = 0; h < H; ++h) {
-        if (h < h_rt) {
-            const float* w = &c->W1[size_t(h) * 4];
-            k.l1[h] = make_float4(c->b1[h], w[0], w[1], w[2]);
-            // separately rounded fp32 products W1[h,3]*t (volatile keeps the compiler from folding
-            // them into anything wider)
-            volatile float pm = w[3] * tcoord[0], p0 = w[3] * tcoord[1], pp = w[3] * tcoord[2];
-            k.lt[h] = make_float4(pm, p0, pp, 0.f);
-            k.w2[h] = make_float4(c->W2[size_t(h_rt) + h], c->W2[h], c->W2[3 * size_t(h_rt) + h], c->W2[2 * size_t(h_rt) + h]);
-        } else {
-            k.l1[h] = k.lt[h] = k.w2[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    auto W1 = [&](int h, int col) { return h < h_rt ? c->W1[size_t(h) * 4 + col] : 0.f; };
+    auto B1 = [&](int h) { return h < h_rt ? c->b1[h] : 0.f; };
+    auto W2 = [&](int o, int h) { return h < h_rt ? c->W2[size_t(o) * h_rt + h] : 0.f; };
+    // separately rounded fp32 product W1[h,3]*t (volatile: nothing wider, nothing fused)
+    auto PT = [&](int h, int s) { volatile float p = W1(h, 3) * tcoord[s]; return float(p); };
+    for (int q = 0; q < H / 2; ++q) {
+        const int h0 = 2 * q, h1 = 2 * q + 1;
+        k.b1p[q] = make_float2(B1(h0), B1(h1));
+        k.w0s[q] = make_float2(W1(h1, 0), W1(h0, 0));
+        k.w1s[q] = make_float2(W1(h1, 1), W1(h0, 1));
+        k.w2s[q] = make_float2(W1(h1, 2), W1(h0, 2));
+        k.ptm[q] = make_float2(PT(h0, 0), PT(h1, 0));
+        k.pt0[q] = make_float2(PT(h0, 1), PT(h1, 1));
+        k.ptp[q] = make_float2(PT(h0, 2), PT(h1, 2));
     }
+    for (int h = 0; h < H; ++h) k.w2[h] = make_float4(W2(1, h), W2(0, h), W2(3, h), W2(2, h));
     k.b2 = make_float4(c->b2[0], c->b2[1], c->b2[2], c->b2[3]);
 }
 
@@ -187,6 +190,8 @@ int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
         case 9: return launch_fused_t<H, 4, 16, 2, 1, true>(c, g, s, tc, dt, acc, R, st);
         case 10: return launch_fused_t<H, 3, 8, 2, 2, true>(c, g, s, tc, dt, acc, R, st);
         case 11: return launch_fused_t<H, 4, 8, 1, 2, true>(c, g, s, tc, dt, acc, R, st);
+        case 12: return launch_fused_t<H, 4, 16, 1, 1, true>(c, g, s, tc, dt, acc, R, st);
+        case 13: return launch_fused_t<H, 2, 16, 2, 1, true>(c, g, s, tc, dt, acc, R, st);
     }
 }
 

@@ -21,13 +21,22 @@
 
 namespace physad {
 
-// Per-hidden-unit records, laid out for 128-bit uniform loads.
+// Weights as the kernels consume them, filled on the host (capi.cu: fill_const) and passed as a
+// __grid_constant__ kernel parameter.  Layer 1 is stored per PAIR of hidden units q = (2q, 2q+1) because
+// it is evaluated two hidden units at a time with packed f32x2 instructions; arrays whose values are
+// multiplied (w0s, w1s, w2s and the layer-2 pairs) hold their pair half-swapped, see mlp_eval.
 template <int H>
 struct MlpConst {
-    float4 l1[H];  // {b1[h], W1[h,0], W1[h,1], W1[h,2]}
-    float4 lt[H];  // {W1[h,3]*t_minus, W1[h,3]*t_0, W1[h,3]*t_plus, 0}   (rounded fp32 products)
-    float4 w2[H];  // {W2[1,h], W2[0,h], W2[3,h], W2[2,h]}  (output pairs stored half-swapped, see mlp_eval)
-    float4 b2;     // {b2[0..3]}
+    static_assert(H % 2 == 0, "hidden units are processed in pairs");
+    float2 b1p[H / 2];  // {b1[2q],   b1[2q+1]}
+    float2 w0s[H / 2];  // {W1[2q+1,0], W1[2q,0]}   swapped
+    float2 w1s[H / 2];  // {W1[2q+1,1], W1[2q,1]}   swapped
+    float2 w2s[H / 2];  // {W1[2q+1,2], W1[2q,2]}   swapped
+    float2 ptm[H / 2];  // {W1[2q,3]*t_minus, W1[2q+1,3]*t_minus}  separately rounded fp32 products
+    float2 pt0[H / 2];  // same for t
+    float2 ptp[H / 2];  // same for t_plus
+    float4 w2[H];       // {W2[1,h], W2[0,h], W2[3,h], W2[2,h]}   output pairs, swapped
+    float4 b2;          // {b2[0..3]}
 };
 
 __device__ __forceinline__ float relu_ref(float s) {
@@ -89,8 +98,18 @@ __device__ __forceinline__ f32x2 add2_rn_swapped(f32x2 acc, f32x2 p) {
     return r;
 }
 
+__device__ __forceinline__ f32x2 add2_rn(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 pack2(float2 v) { return pack2(v.x, v.y); }
+__device__ __forceinline__ f32x2 bcast2(float v) { return pack2(v, v); }  // becomes a `.F32` broadcast operand
+
 // NS = 3: all three time slices (y[j][0|1|2] = t-dt | t | t+dt);  NS = 1: time t only (y[j][0]).
-// P points share cx and cz and differ in cy.  PACKED selects the FMUL2/FADD2 layer 2.
+// P points share cx and cz and differ in cy.
+// PACKED = true : layer 1 on two hidden units per instruction, layer 2 on two outputs per instruction.
+// PACKED = false: the same arithmetic as scalar FMUL/FADD (kept as the in-tree cross-check; bitwise equal).
 template <int H, int NS, int P, int UNROLL, bool PACKED>
 __device__ __forceinline__ void mlp_eval(const MlpConst<H>& w, float cx, const float (&cy)[P], float cz,
                                          float (&y)[P][NS][4]) {
@@ -108,29 +127,51 @@ __device__ __forceinline__ void mlp_eval(const MlpConst<H>& w, float cx, const f
             }
         }
 #pragma unroll UNROLL
-    for (int h = 0; h < H; ++h) {
-        const float4 a = w.l1[h];
-        const float4 tt = w.lt[h];
-        const float4 c = w.w2[h];  // {W2[1,h], W2[0,h], W2[3,h], W2[2,h]}: pairs stored swapped
-        const float sx = __fadd_rn(a.x, __fmul_rn(a.y, cx));  // b1 + W1[h,0]*x
-        const float mz = __fmul_rn(a.w, cz);                  // W1[h,2]*z
-        const f32x2 c10 = pack2(c.x, c.y), c32 = pack2(c.z, c.w);
+    for (int q = 0; q < H / 2; ++q) {
+        const float2 b1p = w.b1p[q], w0s = w.w0s[q], w1s = w.w1s[q], w2s = w.w2s[q];
+        const float2 tm = w.ptm[q], t0 = w.pt0[q], tp = w.ptp[q];
+        const float4 ca = w.w2[2 * q], cb = w.w2[2 * q + 1];
+        if (PACKED) {
+            // {h, h+1} pre-activations; every product is formed half-swapped and added back swapped
+            const f32x2 sx = add2_rn_swapped(pack2(b1p), mul2_rn(pack2(w0s), bcast2(cx)));  // b1 + W1[.,0]*x
+            const f32x2 mz = mul2_rn(pack2(w2s), bcast2(cz));                               // W1[.,2]*z (swapped)
+            const f32x2 ca10 = pack2(ca.x, ca.y), ca32 = pack2(ca.z, ca.w);
+            const f32x2 cb10 = pack2(cb.x, cb.y), cb32 = pack2(cb.z, cb.w);
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-            const float sxyz = __fadd_rn(__fadd_rn(sx, __fmul_rn(a.z, cy[j])), mz);
+            for (int j = 0; j < P; ++j) {
+                const f32x2 sxy = add2_rn_swapped(sx, mul2_rn(pack2(w1s), bcast2(cy[j])));
+                const f32x2 sxyz = add2_rn_swapped(sxy, mz);
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const float pt = (NS == 1) ? tt.y : (s == 0 ? tt.x : (s == 1 ? tt.y : tt.z));
-                const float act = relu_ref(__fadd_rn(sxyz, pt));
-                if (PACKED) {
-                    const f32x2 aa = pack2(act, act);
-                    q01[j][s] = add2_rn_swapped(q01[j][s], mul2_rn(aa, c10));
-                    q23[j][s] = add2_rn_swapped(q23[j][s], mul2_rn(aa, c32));
-                } else {
-                    y[j][s][0] = __fadd_rn(y[j][s][0], __fmul_rn(c.y, act));
-                    y[j][s][1] = __fadd_rn(y[j][s][1], __fmul_rn(c.x, act));
-                    y[j][s][2] = __fadd_rn(y[j][s][2], __fmul_rn(c.w, act));
-                    y[j][s][3] = __fadd_rn(y[j][s][3], __fmul_rn(c.z, act));
+                for (int s = 0; s < NS; ++s) {
+                    const float2 pt = (NS == 1) ? t0 : (s == 0 ? tm : (s == 1 ? t0 : tp));
+                    float v0, v1;
+                    unpack2(add2_rn(sxyz, pack2(pt)), v0, v1);
+                    const f32x2 a0 = bcast2(relu_ref(v0)), a1 = bcast2(relu_ref(v1));
+                    q01[j][s] = add2_rn_swapped(q01[j][s], mul2_rn(a0, ca10));   // h = 2q
+                    q23[j][s] = add2_rn_swapped(q23[j][s], mul2_rn(a0, ca32));
+                    q01[j][s] = add2_rn_swapped(q01[j][s], mul2_rn(a1, cb10));   // h = 2q + 1
+                    q23[j][s] = add2_rn_swapped(q23[j][s], mul2_rn(a1, cb32));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {  // h = 2q + e
+                const float b1 = e ? b1p.y : b1p.x, w0 = e ? w0s.x : w0s.y, w1 = e ? w1s.x : w1s.y, w2 = e ? w2s.x : w2s.y;
+                const float4 c = e ? cb : ca;
+                const float sx = __fadd_rn(b1, __fmul_rn(w0, cx));
+                const float mz = __fmul_rn(w2, cz);
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const float sxyz = __fadd_rn(__fadd_rn(sx, __fmul_rn(w1, cy[j])), mz);
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const float2 pt2 = (NS == 1) ? t0 : (s == 0 ? tm : (s == 1 ? t0 : tp));
+                        const float act = relu_ref(__fadd_rn(sxyz, e ? pt2.y : pt2.x));
+                        y[j][s][0] = __fadd_rn(y[j][s][0], __fmul_rn(c.y, act));
+                        y[j][s][1] = __fadd_rn(y[j][s][1], __fmul_rn(c.x, act));
+                        y[j][s][2] = __fadd_rn(y[j][s][2], __fmul_rn(c.w, act));
+                        y[j][s][3] = __fadd_rn(y[j][s][3], __fmul_rn(c.z, act));
+                    }
                 }
             }
         }
