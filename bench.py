@@ -51,7 +51,7 @@ def strict_fp32_peak():
 
 class ClockSampler:
     """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks
-    line), through NVML in-process every 5 ms (spawning nvidia-smi is slower than the timed region)."""
+    line), through NVML in-process every ~3 ms (spawning nvidia-smi is slower than the timed region)."""
 
     def __init__(self, index: int):
         self.index, self.rows, self.stop_flag, self.th, self.err = index, [], False, None, None
@@ -87,17 +87,24 @@ class ClockSampler:
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.rows.append((sm, pw, rs))
+                self.rows.append((time.perf_counter(), sm, pw, rs))
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 break
-            time.sleep(0.005)
+            time.sleep(0.003)
+
+    def mark(self):
+        """Start of the timed region: only samples from here on are reported (the thread itself is
+        started before warm-up so NVML's first-call latencies never land inside a timed step)."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.th is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + str(self.err)]}
         self.stop_flag = True
         self.th.join(timeout=2)
+        t_mark = getattr(self, "t_mark", 0.0)
+        self.rows = [r[1:] for r in self.rows if r[0] >= t_mark]
         nv = self.nv
         names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
@@ -109,7 +116,7 @@ class ClockSampler:
         busy = [s for s, p in zip(sm, pw) if p >= 0.6 * max(pw)] if pw else []
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": float(self.max_sm),
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_under_load": len(busy),
-                "reasons": reasons}
+                "window": "warm-up + timed steps", "reasons": reasons}
 
 
 def cpu_reference_rate(H: int, nxy: int, planes: int, threads: int):
@@ -181,7 +188,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=-1, help="fused-kernel launch variant (tuning)")
     ap.add_argument("--ref-planes", type=int, default=32, help="z planes per step of the reference arm")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: in-kernel peer-memory all-reduce (default) or kernel + NCCL all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="skip the NVML clock sampler thread (diagnostics)")
     ap.add_argument("--extra", action="store_true", help="also time H=32 and H=128 (reported under 'extra')")
     args = ap.parse_args()
 
@@ -224,17 +234,26 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # multi-GPU: the two partial sums are all-reduced inside the kernel over NVLink peer memory unless
+    # --collective nccl asks for the plain kernel + one NCCL all-reduce of 2 doubles
+    p2p = world > 1 and args.collective == "p2p" and ctx.connect_peers()
+    launch = ctx.prepare_fused(g, T0, DT, slab=slab, acc=acc, allreduce=bool(p2p))   # pre-marshalled C-ABI call
+
     def step():
-        ctx.fused_loss_acc(g, T0, DT, slab=slab, acc=acc)
-        if world > 1:
+        launch()
+        if world > 1 and not p2p:
             dist.all_reduce(acc, op=dist.ReduceOp.SUM)
 
     def timed(K, W, sampler=None):
+        if sampler:  # sampling window = warm-up + timed steps (same kernel, same load); NVML's slow first
+            sampler.start()   # calls happen before any timed step
+            t_wait = time.perf_counter()
+            while not sampler.rows and sampler.th is not None and time.perf_counter() - t_wait < 0.5:
+                time.sleep(0.001)
+            sampler.mark()
         for _ in range(W):
             step()
         barrier()
-        if sampler:
-            sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         l0 = ctx.launch_count
         wall0 = time.perf_counter()
@@ -250,9 +269,13 @@ def main():
         tot = torch.tensor([sum(per)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+            allper = [None] * world
+            dist.all_gather_object(allper, per)
+            timed.per_rank = [{"sum_ms": sum(p), "median": statistics.median(p), "max": max(p),
+                               "n_over_1.2x_median": sum(1 for v in p if v > 1.2 * statistics.median(p))} for p in allper]
         return tot.item(), per, ctx.launch_count - l0, clocks, wall
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
     total_ms, per, launches, clocks, wall = timed(args.steps, max(3, args.warmup), sampler)
     value = g.N * args.steps / (total_ms * 1e-3)
     ls, lu = ctx.finalize(acc.cpu().numpy(), pw, g.N)
@@ -319,7 +342,8 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"fused MLP(4-{H}-4)+phys loss, {n}^3 grid, seed {SEED}, scale {SCALE}, t {T0}, dt {DT}, "
                                    f"h 1, periodic, MinusOneToOne (test_mlp_phys_perf.cpp:21-23 at 256^3)",
-                       "hidden": H, "grid": [n, n, n], "parallelism": f"z-slab x{world}, halo recomputed, 1 all-reduce of 2 doubles",
+                       "hidden": H, "grid": [n, n, n], "parallelism": f"z-slab x{world}, halo recomputed, 1 all-reduce of 2 doubles "
+                                      + ("inside the kernel over NVLink peer memory" if p2p else "(NCCL)" if world > 1 else "(n/a)"),
                        "mode": "strict fp32 (FMUL+FADD, bit-exact MLP)",
                        "l2": "no HBM-resident inputs (coordinates from index, weights in the constant bank); L2 flushed "
                              "between timed steps with a 256 MiB write outside the per-step events",
@@ -337,6 +361,8 @@ def main():
                                  "non-contracted FMUL+FADD rate (parity mode cannot use FFMA); HBM traffic is ~0 by design"},
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall,
+            "step_ms": {"min": min(per), "median": statistics.median(per), "max": max(per)},
+            "per_rank": getattr(timed, "per_rank", None),
         }
         if extra:
             line["extra"] = extra

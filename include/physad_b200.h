@@ -165,6 +165,23 @@ int physad_fused_loss_host(physad_ctx* ctx, const physad_grid* g, const physad_m
                            const float* b1, const float* W2, const float* b2, const physad_phys_weights* w, float t,
                            float dt, float* loss_sigma, float* loss_u, float* R_sigma, float* R_ux, float* R_uy,
                            float* R_uz);
+/* ---- multi-GPU: the same kernel with the all-reduce of the two sums done INSIDE it, over NVLink
+ * peer memory (SURVEY.md section 8e asks for one collective of 2 doubles; this removes its launch).
+ * Setup once per process group (one process per GPU, ranks of one node, world <= 8):
+ *   1. every rank: physad_xchg_export(ctx, handle)            -> 64-byte CUDA IPC handle of its exchange buffer
+ *   2. all-gather the handles with whatever the host uses (torch.distributed, MPI, a file ...)
+ *   3. every rank: physad_xchg_connect(ctx, rank, world, handles)   -- handles: world x 64 bytes, in rank order
+ * Then physad_fused_loss_allreduce_dev behaves like physad_fused_loss_dev, except that acc_dev
+ * receives the GLOBAL sums on every rank (added in rank order: identical bits everywhere).  All ranks
+ * must make the same sequence of these calls (one exchange epoch per call), slab empty or not.  A rank
+ * that never arrives makes the others return NaN after ~4 s instead of hanging. */
+#define PHYSAD_XCHG_HANDLE_BYTES 64
+int physad_xchg_export(physad_ctx* ctx, void* handle_out);
+int physad_xchg_connect(physad_ctx* ctx, int rank, int world, const void* handles);
+int physad_xchg_disconnect(physad_ctx* ctx);
+int physad_fused_loss_allreduce_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float dt,
+                                    double* acc_dev, float* R_sigma, float* R_ux, float* R_uy, float* R_uz, void* stream);
+
 /* L = float(w * acc * (1.0 / N_global)) exactly as src/phys_cpu.cpp:146-148.  Pure host arithmetic. */
 void physad_finalize_loss(const double acc[2], const physad_phys_weights* w, size_t n_global, float* loss_sigma,
                           float* loss_u);

@@ -49,6 +49,11 @@ struct physad_ctx {
     size_t scratch_cap = 0;
     uint64_t launches = 0;
     int fused_variant = 0;
+    // multi-GPU exchange through peer memory (physad_xchg_*)
+    XSlot* xbuf = nullptr;                       // own buffer: [2][XCHG_MAX_RANKS] slots
+    XSlot* xpeer[XCHG_MAX_RANKS] = {};           // every rank's buffer as mapped in this process
+    int xrank = 0, xworld = 1;
+    unsigned long long xepoch = 0;
 };
 
 namespace {
@@ -136,25 +141,29 @@ struct FusedGeom {
 };
 
 template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED>
-int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], float dt, double* acc,
+int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool xchg, double* acc,
                    float* const R[4], cudaStream_t st) {
     constexpr int TX = 32, TY = TYB * P;
     auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB, PACKED>;
     const size_t smem = size_t(4) * 4 * (TX + 2) * (TY + 2) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // per-kernel launch facts, queried once per process (this sits on the per-step host path)
+    static int per_sm = 0;
+    static long long env_blocks = -1;
+    if (per_sm == 0) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        attr_done = true;
+        int q = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, 32 * TYB, smem));
+        if (q < 1) return fail(PHYSAD_E_UNSUPPORTED, "fused kernel does not fit on an SM");
+        const char* e = getenv("PHYSAD_FUSED_BLOCKS");
+        env_blocks = e ? atoll(e) : 0;
+        per_sm = q;
     }
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * TYB, smem));
-    if (per_sm < 1) return fail(PHYSAD_E_UNSUPPORTED, "fused kernel does not fit on an SM");
     const int tiles_x = (g->nx + TX - 1) / TX, tiles_y = (g->ny + TY - 1) / TY;
     const int tiles = tiles_x * tiles_y, nzl = s.z_end - s.z_begin;
     // persistent grid: one block per resident slot, each owning an equal share of the tile-planes
     const long long slots = (long long)per_sm * c->sm_count, work = (long long)tiles * nzl;
     long long blocks = std::min(slots, work);
-    if (const char* e = getenv("PHYSAD_FUSED_BLOCKS")) blocks = std::max(1LL, std::min(work, atoll(e)));
+    if (env_blocks > 0) blocks = std::max(1LL, std::min(work, env_blocks));
     FusedArgs a{};
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
     a.z_begin = s.z_begin; a.z_end = s.z_end;
@@ -164,9 +173,12 @@ int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
     if (int rc = ensure_partials(c, size_t(blocks))) return rc;
     a.partials = c->partials; a.ticket = c->ticket; a.acc_out = acc;
     for (int k = 0; k < 4; ++k) a.R[k] = R[k];
+    if (xchg) {
+        a.x.rank = c->xrank; a.x.world = c->xworld; a.x.epoch = c->xepoch;
+        for (int p = 0; p < XCHG_MAX_RANKS; ++p) a.x.peer[p] = c->xpeer[p];
+    }
     MlpConst<H> k;
     fill_const<H>(c, tc, k);
-    (void)dt;
     kern<<<unsigned(blocks), 32 * TYB, smem, st>>>(k, a);
     c->launches++;
     CU(cudaGetLastError());
@@ -174,39 +186,47 @@ int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
 }
 
 template <int H>
-int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], float dt, double* acc,
+int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool dt, double* acc,
                    float* const R[4], cudaStream_t st) {
+    // <H, P columns/thread, warps/block, unroll (pairs of hidden units), min blocks/SM, packed>
     switch (c->fused_variant) {
         default:
-        case 0: return launch_fused_t<H, 4, 8, 2, 1, true>(c, g, s, tc, dt, acc, R, st);
-        case 1: return launch_fused_t<H, 2, 8, 4, 2, true>(c, g, s, tc, dt, acc, R, st);
-        case 2: return launch_fused_t<H, 2, 16, 4, 1, true>(c, g, s, tc, dt, acc, R, st);
-        case 3: return launch_fused_t<H, 4, 8, 2, 1, false>(c, g, s, tc, dt, acc, R, st);   // scalar layer 2 (round-1 first cut)
-        case 4: return launch_fused_t<H, 4, 8, 4, 1, true>(c, g, s, tc, dt, acc, R, st);
-        case 5: return launch_fused_t<H, 1, 8, 4, 4, true>(c, g, s, tc, dt, acc, R, st);
-        case 6: return launch_fused_t<H, 2, 8, 2, 3, true>(c, g, s, tc, dt, acc, R, st);
-        case 7: return launch_fused_t<H, 4, 4, 2, 2, true>(c, g, s, tc, dt, acc, R, st);
-        case 8: return launch_fused_t<H, 4, 8, 2, 2, true>(c, g, s, tc, dt, acc, R, st);
-        case 9: return launch_fused_t<H, 4, 16, 2, 1, true>(c, g, s, tc, dt, acc, R, st);
-        case 10: return launch_fused_t<H, 3, 8, 2, 2, true>(c, g, s, tc, dt, acc, R, st);
-        case 11: return launch_fused_t<H, 4, 8, 1, 2, true>(c, g, s, tc, dt, acc, R, st);
-        case 12: return launch_fused_t<H, 4, 16, 1, 1, true>(c, g, s, tc, dt, acc, R, st);
-        case 13: return launch_fused_t<H, 2, 16, 2, 1, true>(c, g, s, tc, dt, acc, R, st);
+        case 0: return launch_fused_t<H, 4, 8, 2, 2, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x32, 2 x 256 threads/SM
+        case 1: return launch_fused_t<H, 4, 16, 2, 1, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x64, 1 x 512 threads/SM
+        case 2: return launch_fused_t<H, 4, 16, 1, 1, true>(c, g, s, tc, dt, acc, R, st);
+        case 3: return launch_fused_t<H, 4, 8, 2, 1, false>(c, g, s, tc, dt, acc, R, st);   // scalar FMUL/FADD cross-check
+        case 4: return launch_fused_t<H, 2, 16, 4, 1, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x32, 1 x 512
+        case 5: return launch_fused_t<H, 1, 8, 4, 4, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x8
+        case 6: return launch_fused_t<H, 2, 8, 2, 3, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x16, 3 x 256
+        case 7: return launch_fused_t<H, 4, 8, 1, 2, true>(c, g, s, tc, dt, acc, R, st);
     }
 }
 
 int launch_fused(physad_ctx* c, const physad_grid* g, const physad_slab& s, float t, float dt, double* acc,
-                 float* const R[4], cudaStream_t st) {
-    if (s.z_end == s.z_begin) {  // empty slab: the sum over nothing
-        CU(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+                 float* const R[4], cudaStream_t st, bool xchg = false) {
+    if (xchg) {
+        if (c->xworld <= 1 || !c->xbuf) return fail(PHYSAD_E_INVALID, "fused_loss_allreduce: call physad_xchg_connect first");
+        c->xepoch++;  // every rank makes the same sequence of calls, so epochs agree
+    }
+    if (s.z_end == s.z_begin) {  // empty slab: the sum over nothing (still takes part in the exchange)
+        if (!xchg) {
+            CU(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+            return 0;
+        }
+        XchgArgs x{};
+        x.rank = c->xrank; x.world = c->xworld; x.epoch = c->xepoch;
+        for (int p = 0; p < XCHG_MAX_RANKS; ++p) x.peer[p] = c->xpeer[p];
+        k_xchg_only<<<1, 32, 0, st>>>(x, acc);
+        c->launches++;
+        CU(cudaGetLastError());
         return 0;
     }
     const float ts[3] = {t - dt, t, t + dt};  // as src/mlp_grid.cpp:87-89
     const float tc[3] = {time_coord(ts[0], c->cfg.norm), time_coord(ts[1], c->cfg.norm), time_coord(ts[2], c->cfg.norm)};
     switch (template_h(c->cfg.H)) {
-        case 32: return launch_fused_h<32>(c, g, s, tc, dt, acc, R, st);
-        case 64: return launch_fused_h<64>(c, g, s, tc, dt, acc, R, st);
-        case 128: return launch_fused_h<128>(c, g, s, tc, dt, acc, R, st);
+        case 32: return launch_fused_h<32>(c, g, s, tc, xchg, acc, R, st);
+        case 64: return launch_fused_h<64>(c, g, s, tc, xchg, acc, R, st);
+        case 128: return launch_fused_h<128>(c, g, s, tc, xchg, acc, R, st);
     }
     return fail(PHYSAD_E_UNSUPPORTED, "H > 128 not built");
 }
@@ -331,6 +351,8 @@ int physad_ctx_destroy(physad_ctx* c) {
     DeviceGuard dg(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->dW1); cudaFree(c->db1); cudaFree(c->dW2); cudaFree(c->db2);
+    physad_xchg_disconnect(c);
+    cudaFree(c->xbuf);
     cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_acc); cudaFree(c->scratch);
     cudaFreeHost(c->h_acc);
     cudaStreamDestroy(c->stream);
@@ -672,6 +694,65 @@ int physad_fused_loss_dev(physad_ctx* c, const physad_grid* g, const physad_slab
     DeviceGuard dg(c->device);
     float* R[4] = {Rs, Rx, Ry, Rz};
     return launch_fused(c, g, s, t, dt, acc, R, cudaStream_t(stream));
+}
+
+int physad_fused_loss_allreduce_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, float t, float dt,
+                                    double* acc, float* Rs, float* Rx, float* Ry, float* Rz, void* stream) {
+    if (!c || !acc) return fail(PHYSAD_E_INVALID, "fused_loss_allreduce: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = need_4x4(c, "fused_loss_allreduce")) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    const bool any = Rs || Rx || Ry || Rz, all = Rs && Rx && Ry && Rz;
+    if (any && !all) return fail(PHYSAD_E_INVALID, "fused_loss_allreduce: residual outputs must be all set or all null");
+    DeviceGuard dg(c->device);
+    float* R[4] = {Rs, Rx, Ry, Rz};
+    return launch_fused(c, g, s, t, dt, acc, R, cudaStream_t(stream), true);
+}
+
+int physad_xchg_export(physad_ctx* c, void* handle_out) {
+    if (!c || !handle_out) return fail(PHYSAD_E_INVALID, "xchg_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PHYSAD_XCHG_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard dg(c->device);
+    if (!c->xbuf) {
+        CU(cudaMalloc(&c->xbuf, 2 * XCHG_MAX_RANKS * sizeof(XSlot)));
+        CU(cudaMemset(c->xbuf, 0, 2 * XCHG_MAX_RANKS * sizeof(XSlot)));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->xbuf));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int physad_xchg_connect(physad_ctx* c, int rank, int world, const void* handles) {
+    if (!c || !handles) return fail(PHYSAD_E_INVALID, "xchg_connect: null argument");
+    if (world < 1 || world > XCHG_MAX_RANKS || rank < 0 || rank >= world)
+        return fail(PHYSAD_E_UNSUPPORTED, "xchg_connect: 1 <= world <= 8 ranks of one node");
+    if (!c->xbuf) return fail(PHYSAD_E_INVALID, "xchg_connect: call physad_xchg_export first");
+    DeviceGuard dg(c->device);
+    physad_xchg_disconnect(c);
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) { c->xpeer[p] = c->xbuf; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + size_t(p) * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->xpeer[p] = static_cast<XSlot*>(ptr);
+    }
+    CU(cudaMemset(c->xbuf, 0, 2 * XCHG_MAX_RANKS * sizeof(XSlot)));
+    CU(cudaDeviceSynchronize());
+    c->xrank = rank; c->xworld = world; c->xepoch = 0;
+    return 0;
+}
+
+int physad_xchg_disconnect(physad_ctx* c) {
+    if (!c) return 0;
+    for (int p = 0; p < XCHG_MAX_RANKS; ++p) {
+        if (c->xpeer[p] && c->xpeer[p] != c->xbuf) cudaIpcCloseMemHandle(c->xpeer[p]);
+        c->xpeer[p] = nullptr;
+    }
+    c->xworld = 1; c->xrank = 0; c->xepoch = 0;
+    return 0;
 }
 
 int physad_fused_loss_host(physad_ctx* c, const physad_grid* g, const physad_mlp_config* cfg, const float* W1,

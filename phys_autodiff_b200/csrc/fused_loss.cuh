@@ -30,6 +30,79 @@
 
 namespace physad {
 
+// ---- in-kernel all-reduce of the two partial sums over NVLink peer memory ------------------------
+// Each rank owns an exchange buffer of XCHG_MAX_RANKS x 2 slots that every peer has mapped (CUDA IPC,
+// capi.cu: physad_xchg_*).  The last block of rank r stores its {sum_s, sum_u} into slot [epoch&1][r] of
+// EVERY rank's buffer (plain P2P stores, then a system-scope release of the slot's flag = epoch), waits
+// until all `world` slots of its own buffer carry this epoch, and adds them in rank order -- so every
+// rank ends the kernel with the same, deterministic global sums and no separate collective launch
+// (NCCL's latency for a 16-byte all-reduce is a sizeable fraction of a ~0.15 ms slab kernel).
+// Two slot sets (epoch parity) suffice: a rank can only be one epoch ahead of the slowest peer,
+// because finishing epoch e needs every peer's epoch-e flag.  Ranks are one process per GPU, so the
+// kernels that wait on each other run on different devices.
+constexpr int XCHG_MAX_RANKS = 8;
+
+struct XSlot {
+    double a, b;
+    unsigned long long flag;
+    unsigned long long pad;
+};
+
+struct XchgArgs {
+    int rank, world;               // world <= 1: exchange disabled
+    unsigned long long epoch;      // same on every rank, > 0, +1 per launch
+    XSlot* peer[XCHG_MAX_RANKS];   // peer[p] = rank p's buffer as mapped here (peer[rank] = own)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by the first warp of one block with this rank's totals; returns the global totals in (a, b)
+// on lane 0.  A peer that never shows up (crashed rank) ends the wait after ~4 s with NaN results
+// instead of hanging the GPU.
+__device__ __forceinline__ void xchg_allreduce2(const XchgArgs& x, double& a, double& b) {
+    const int lane = threadIdx.x & 31;
+    const int set = int(x.epoch & 1ull) * XCHG_MAX_RANKS;
+    if (lane < x.world) {
+        XSlot* s = x.peer[lane] + set + x.rank;
+        s->a = a;
+        s->b = b;
+        __threadfence_system();
+        st_release_sys(&s->flag, x.epoch);
+    }
+    bool ok = true;
+    if (lane < x.world) {
+        const XSlot* s = x.peer[x.rank] + set + lane;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&s->flag) != x.epoch) {
+            if (clock64() - t0 > 8000000000ll) { ok = false; break; }
+            __nanosleep(64);
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int p = 0; p < x.world; ++p) {
+            const XSlot* s = x.peer[x.rank] + set + p;
+            ta += ld_relaxed_sys(&s->a);
+            tb += ld_relaxed_sys(&s->b);
+        }
+        a = ok ? ta : __longlong_as_double(0x7ff8000000000000ll);
+        b = ok ? tb : __longlong_as_double(0x7ff8000000000000ll);
+    }
+}
+
 struct FusedArgs {
     int nx, ny, nz;          // global grid
     int z_begin, z_end;      // slab [z_begin, z_end)
@@ -40,6 +113,7 @@ struct FusedArgs {
     unsigned int* ticket;    // zero on entry, zero again on exit
     double* acc_out;         // [2]
     float* R[4];             // slab-local residual outputs or null
+    XchgArgs x;              // multi-GPU exchange (world <= 1: off)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -51,7 +125,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Block-wide {a,b} sum -> per-block partial -> grid total written by the last block to finish.
 template <int NWARPS>
 __device__ __forceinline__ void grid_reduce2(double a, double b, double2* partials, unsigned int* ticket, double* out,
-                                             double2* s_red, unsigned int* s_flag) {
+                                             double2* s_red, unsigned int* s_flag, const XchgArgs* x = nullptr) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     a = warp_sum(a);
     b = warp_sum(b);
@@ -79,14 +153,25 @@ __device__ __forceinline__ void grid_reduce2(double a, double b, double2* partia
     __syncthreads();
     if (lane == 0) s_red[wid] = make_double2(sa, sb);
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {  // first warp: block total, optional cross-rank exchange, publish
         double ta = 0.0, tb = 0.0;
 #pragma unroll
         for (int i = 0; i < NWARPS; ++i) { ta += s_red[i].x; tb += s_red[i].y; }
-        out[0] = ta;
-        out[1] = tb;
-        *ticket = 0u;
+        if (x != nullptr && x->world > 1) xchg_allreduce2(*x, ta, tb);
+        if (threadIdx.x == 0) {
+            out[0] = ta;
+            out[1] = tb;
+            *ticket = 0u;
+        }
     }
+}
+
+// Exchange-only launch for a rank whose slab is empty (more ranks than planes): it still has to
+// contribute its zeros and must end up with the global sums.
+__global__ void k_xchg_only(const XchgArgs x, double* out) {
+    double a = 0.0, b = 0.0;
+    xchg_allreduce2(x, a, b);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
 }
 
 template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED>
@@ -232,7 +317,7 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
     // The next segment starts writing plane buffers that the slowest warp may still be reading.
     __syncthreads();
   }
-    grid_reduce2<NWARPS>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag);
+    grid_reduce2<NWARPS>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag, &a.x);
 }
 
 }  // namespace physad

@@ -38,6 +38,7 @@ class Context:
         self._h = C.c_void_p()
         check(self._lib.physad_ctx_create(C.byref(self._h), C.c_int(-1 if device is None else device)), "ctx_create")
         self.cfg: Optional[MLPConfig] = None
+        self._peers = None  # (rank, world) once connect_peers() has mapped the peers' exchange buffers
 
     def close(self):
         if self._h:
@@ -61,6 +62,28 @@ class Context:
 
     def set_fused_variant(self, v: int) -> int:
         return int(self._lib.physad_set_fused_variant(self._h, C.c_int(v)))
+
+    def connect_peers(self, group=None) -> bool:
+        """Map every rank's exchange buffer (CUDA IPC over NVLink) so the fused kernel can all-reduce its
+        two sums itself.  torch.distributed is used only to all-gather the 64-byte handles.  Returns
+        False (and leaves the NCCL path in place) for a single rank."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return False
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = C.create_string_buffer(64)
+        check(self._lib.physad_xchg_export(self._h, buf), "xchg_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(buf.raw), group=group)
+        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        check(self._lib.physad_xchg_connect(self._h, C.c_int(rank), C.c_int(world), blob), "xchg_connect")
+        dist.barrier(group)  # nobody launches an exchange before every rank has mapped every buffer
+        self._peers = (rank, world)
+        return True
+
+    def disconnect_peers(self) -> None:
+        self._lib.physad_xchg_disconnect(self._h)
+        self._peers = None
 
     def set_weights(self, cfg: MLPConfig, W1, b1, W2, b2) -> None:
         W1, b1, W2, b2 = _f32(W1), _f32(b1), _f32(W2), _f32(b2)
@@ -162,6 +185,29 @@ class Context:
                                               *[ptr(r) for r in R], self._stream()), "fused_loss")
         return acc
 
+    def prepare_fused(self, g: Grid, t: float, dt: float, slab=None, acc=None, residuals=None, allreduce=False):
+        """Pre-marshal one fused launch (ctypes structs, pointers) and return a zero-argument callable that
+        enqueues it on the current stream: the per-step host cost matters once a slab takes ~0.2 ms.
+        allreduce=True uses the in-kernel peer-memory all-reduce (needs connect_peers())."""
+        import torch
+        cs, _ = self._slab(g, slab)
+        if acc is None:
+            acc = self._empty(2, torch.float64)
+        R = residuals if residuals is not None else [None] * 4
+        cg = g.c()
+        if allreduce and not self._peers:
+            raise capi.PhysadError("prepare_fused(allreduce=True) needs connect_peers() first")
+        fn, h = (self._lib.physad_fused_loss_allreduce_dev if allreduce else self._lib.physad_fused_loss_dev), self._h
+        args = (C.byref(cg), C.byref(cs), C.c_float(t), C.c_float(dt), ptr(acc), *[ptr(r) for r in R])
+        keep = (cg, cs, acc, R)
+
+        def launch(_keep=keep):
+            rc = fn(h, *args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if rc:
+                check(rc, "fused_loss")
+            return acc
+        return launch
+
     def finalize(self, acc, pw: PhysWeights, n_global: int):
         a = (C.c_double * 2)(float(acc[0]), float(acc[1]))
         ls, lu = C.c_float(), C.c_float()
@@ -179,9 +225,12 @@ class Context:
         slab = slab_for_rank(g.nz, rank, world)
         n = (slab[1] - slab[0]) * g.ny * g.nx
         R = [self._empty(n) for _ in range(4)] if want_residuals else None
-        acc = self.fused_loss_acc(g, t, dt, slab=slab, residuals=R)
-        if world > 1:
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        if world > 1 and self._peers == (rank, world):
+            acc = self.prepare_fused(g, t, dt, slab=slab, residuals=R, allreduce=True)()   # exchange inside the kernel
+        else:
+            acc = self.fused_loss_acc(g, t, dt, slab=slab, residuals=R)
+            if world > 1:
+                dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
         ls, lu = self.finalize(acc.cpu().numpy(), pw, g.N)
         return (ls, lu, tuple(R)) if want_residuals else (ls, lu)
 
