@@ -49,6 +49,15 @@ struct physad_ctx {
     size_t scratch_cap = 0;
     uint64_t launches = 0;
     int fused_variant = 0;
+    // launch plan of the fused kernel: coordinate tables + per-block work ranges, cached per geometry
+    struct FusedPlan {
+        int key[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // nx, ny, nz, z_begin, z_end, norm, TX, TY, slots, valid
+        char* dev = nullptr;
+        size_t cap = 0;
+        const float *cxs = nullptr, *cys = nullptr, *czs = nullptr;
+        const int* ranges = nullptr;
+        int blocks = 0;
+    } plan;
     // multi-GPU exchange through peer memory (physad_xchg_*)
     XSlot* xbuf = nullptr;                       // own buffer: [2][XCHG_MAX_RANKS] slots
     XSlot* xpeer[XCHG_MAX_RANKS] = {};           // every rank's buffer as mapped in this process
@@ -135,6 +144,90 @@ int need_4x4(const physad_ctx* c, const char* what) {
 }
 
 // ---- fused kernel launch -----------------------------------------------------------------
+// Axis coordinate exactly as the reference forms it (src/mlp_grid.cpp:25-29; this TU is compiled
+// with -ffp-contract=off): u = float(i)/float(n-1), MinusOneToOne -> 2u-1.
+float host_axis_coord(int i, int n, bool m1p1) {
+    if (n <= 1) return 0.0f;
+    volatile float u = float(i) / float(n - 1);
+    volatile float two_u = 2.f * u;
+    return m1p1 ? two_u - 1.f : float(u);
+}
+
+// Split the tile-plane sequence (tiles x nzl planes, tile-major) into at most `slots` contiguous ranges
+// of equal COST, where a range pays `seg_cost` extra for every z-segment it starts (its two time-t-only
+// halo planes + prologue).  Greedy fill under a cost cap, cap found by bisection.
+std::vector<int> balanced_ranges(int tiles, int nzl, long long slots, double seg_cost) {
+    auto fill = [&](double cap, std::vector<int>* out) {
+        long long blocks = 0;
+        double cur = 0.0;
+        bool open = false;
+        if (out) { out->clear(); out->push_back(0); }
+        for (int t = 0; t < tiles; ++t) {
+            int rem = nzl;
+            while (rem > 0) {
+                const double space = cap - cur - seg_cost;
+                if (space < 1.0 && open) {  // cannot start a segment here: close the block
+                    ++blocks; cur = 0.0; open = false;
+                    if (out) out->push_back(t * nzl + (nzl - rem));
+                    continue;
+                }
+                const int take = std::max(1, std::min(rem, int(space)));
+                cur += seg_cost + take;
+                rem -= take;
+                open = true;
+                if (cur + seg_cost + 1.0 > cap) {
+                    ++blocks; cur = 0.0; open = false;
+                    if (out) out->push_back(t * nzl + (nzl - rem));
+                }
+            }
+        }
+        if (open) { ++blocks; if (out) out->push_back(tiles * nzl); }
+        return blocks;
+    };
+    double lo = 1.0 + seg_cost, hi = double(tiles) * (nzl + seg_cost) + 1.0;
+    for (int it = 0; it < 60; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (fill(mid, nullptr) <= slots) hi = mid; else lo = mid;
+    }
+    std::vector<int> r;
+    fill(hi, &r);
+    return r;
+}
+
+int build_fused_plan(physad_ctx* c, const physad_grid* g, const physad_slab& s, int TX, int TY, long long slots,
+                     cudaStream_t st) {
+    const int key[10] = {g->nx, g->ny, g->nz, s.z_begin, s.z_end, c->cfg.norm, TX, TY, int(slots), 1};
+    auto& p = c->plan;
+    if (std::memcmp(key, p.key, sizeof(key)) == 0) return 0;
+    const bool m1p1 = c->cfg.norm == 1;
+    const int tiles = ((g->nx + TX - 1) / TX) * ((g->ny + TY - 1) / TY), nzl = s.z_end - s.z_begin;
+    long long want = std::min<long long>(slots, (long long)tiles * nzl);
+    std::vector<int> ranges = balanced_ranges(tiles, nzl, want, 0.9);
+    const size_t nf = size_t(g->nx) + g->ny + g->nz;
+    std::vector<char> host(nf * sizeof(float) + ranges.size() * sizeof(int));
+    float* f = reinterpret_cast<float*>(host.data());
+    for (int i = 0; i < g->nx; ++i) f[i] = host_axis_coord(i, g->nx, m1p1);
+    for (int i = 0; i < g->ny; ++i) f[g->nx + i] = host_axis_coord(i, g->ny, m1p1);
+    for (int i = 0; i < g->nz; ++i) f[g->nx + g->ny + i] = host_axis_coord(i, g->nz, m1p1);
+    std::memcpy(host.data() + nf * sizeof(float), ranges.data(), ranges.size() * sizeof(int));
+    if (host.size() > p.cap) {
+        if (p.dev) CU(cudaFree(p.dev));
+        p.dev = nullptr; p.cap = 0;
+        CU(cudaMalloc(&p.dev, host.size()));
+        p.cap = host.size();
+    }
+    // rare (geometry change): a synchronous copy keeps the pageable staging vector's lifetime trivial
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(p.dev, host.data(), host.size(), cudaMemcpyHostToDevice));
+    p.cxs = reinterpret_cast<const float*>(p.dev);
+    p.cys = p.cxs + g->nx;
+    p.czs = p.cys + g->ny;
+    p.ranges = reinterpret_cast<const int*>(p.dev + nf * sizeof(float));
+    p.blocks = int(ranges.size()) - 1;
+    std::memcpy(p.key, key, sizeof(key));
+    return 0;
+}
+
 struct FusedGeom {
     int tiles_x, tiles_y, nchunks;
     size_t smem;
@@ -159,15 +252,15 @@ int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
         per_sm = q;
     }
     const int tiles_x = (g->nx + TX - 1) / TX, tiles_y = (g->ny + TY - 1) / TY;
-    const int tiles = tiles_x * tiles_y, nzl = s.z_end - s.z_begin;
-    // persistent grid: one block per resident slot, each owning an equal share of the tile-planes
-    const long long slots = (long long)per_sm * c->sm_count, work = (long long)tiles * nzl;
-    long long blocks = std::min(slots, work);
-    if (env_blocks > 0) blocks = std::max(1LL, std::min(work, env_blocks));
+    // persistent grid: one block per resident slot, each owning an equal-cost share of the tile-planes
+    const long long slots = env_blocks > 0 ? env_blocks : (long long)per_sm * c->sm_count;
+    if (int rc = build_fused_plan(c, g, s, TX, TY, slots, st)) return rc;
+    const long long blocks = c->plan.blocks;
     FusedArgs a{};
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
     a.z_begin = s.z_begin; a.z_end = s.z_end;
     a.tiles_x = tiles_x; a.tiles_y = tiles_y;
+    a.cxs = c->plan.cxs; a.cys = c->plan.cys; a.czs = c->plan.czs; a.ranges = c->plan.ranges;
     a.m1p1 = c->cfg.norm == 1; a.periodic = g->periodic != 0;
     a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
     if (int rc = ensure_partials(c, size_t(blocks))) return rc;
@@ -353,6 +446,7 @@ int physad_ctx_destroy(physad_ctx* c) {
     cudaFree(c->dW1); cudaFree(c->db1); cudaFree(c->dW2); cudaFree(c->db2);
     physad_xchg_disconnect(c);
     cudaFree(c->xbuf);
+    cudaFree(c->plan.dev);
     cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_acc); cudaFree(c->scratch);
     cudaFreeHost(c->h_acc);
     cudaStreamDestroy(c->stream);

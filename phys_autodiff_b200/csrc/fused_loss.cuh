@@ -5,7 +5,9 @@
 //   work   = tiles x planes "tile-planes", linearised tile-major.  The grid is PERSISTENT: one block per
 //            resident slot (SMs x blocks/SM), block b owns the contiguous range [b W/G, (b+1) W/G) of
 //            tile-planes, i.e. at most two z-segments of (usually) two different tiles -- every block
-//            gets the same number of planes (+-1), so there is no partial last wave.
+//            gets the same COST (planes + the two time-t-only halo planes of every segment it starts;
+//            ranges are computed on the host, capi.cu: FusedPlan), so there is no partial last wave and
+//            no block that is slow because its range straddles two tiles.
 //   block  = marches along z over each of its segments of one (TX x TY) tile of (x,y) columns.
 //   thread = P columns that share x (rows ty, ty+TYB, ...); 32 lanes of a warp = 32 consecutive x.
 //   step k = plane zk = chunk_begin - 1 + k.  Interior steps evaluate all three time slices for
@@ -107,6 +109,11 @@ struct FusedArgs {
     int nx, ny, nz;          // global grid
     int z_begin, z_end;      // slab [z_begin, z_end)
     int tiles_x, tiles_y;    // tile grid; work = tiles_x*tiles_y*(z_end-z_begin) tile-planes over gridDim.x blocks
+    // launch plan (device memory, built once per geometry by capi.cu: FusedPlan)
+    const float* cxs;        // [nx] axis coordinates of x indices (same fp32 ops as the reference, done on the host)
+    const float* cys;        // [ny]
+    const float* czs;        // [nz]
+    const int* ranges;       // [gridDim.x + 1] block b owns tile-planes [ranges[b], ranges[b+1]) -- equal COST shares
     int m1p1, periodic;
     float inv2dt, inv2hx, inv2hy, inv2hz;
     double2* partials;       // [gridDim.x]
@@ -186,12 +193,13 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
     __shared__ unsigned int s_flag;
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // warp id == ty
-    const bool m1p1 = a.m1p1 != 0, per = a.periodic != 0;
+    const bool per = a.periodic != 0;
 
     const int nzl = a.z_end - a.z_begin;
     const long long W = (long long)a.tiles_x * a.tiles_y * nzl;
-    const long long w_end = W * (blockIdx.x + 1) / gridDim.x;
-    long long wpos = W * blockIdx.x / gridDim.x;
+    (void)W;
+    const long long w_end = a.ranges[blockIdx.x + 1];
+    long long wpos = a.ranges[blockIdx.x];
     double acc_s = 0.0, acc_u = 0.0;
     int kbuf = 0;  // running plane-buffer index (keeps rotating across segments)
 
@@ -205,13 +213,13 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
 
     // this thread's columns
     const int gx = x0 + tx;
-    const float cx = axis_coord(bc_index(gx, a.nx, per), a.nx, m1p1);
+    const float cx = __ldg(a.cxs + bc_index(gx, a.nx, per));
     float cy[P];
     bool live[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
         const int gy = y0 + ty + j * TYB;
-        cy[j] = axis_coord(bc_index(gy, a.ny, per), a.ny, m1p1);
+        cy[j] = __ldg(a.cys + bc_index(gy, a.ny, per));
         live[j] = gx < a.nx && gy < a.ny;
     }
     // this lane's ring columns (one per task), fixed for the whole march
@@ -226,8 +234,8 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
         else if (r < 2 * TX + TY) { xx = 0; yy = 1 + r - 2 * TX; }
         else { xx = SX - 1; yy = 1 + r - 2 * TX - TY; }
         if (r >= RING) { xx = 0; yy = 0; }  // idle lane of the last task: harmless duplicate slot
-        rcx[i] = axis_coord(bc_index(x0 - 1 + xx, a.nx, per), a.nx, m1p1);
-        rcy[i] = axis_coord(bc_index(y0 - 1 + yy, a.ny, per), a.ny, m1p1);
+        rcx[i] = __ldg(a.cxs + bc_index(x0 - 1 + xx, a.nx, per));
+        rcy[i] = __ldg(a.cys + bc_index(y0 - 1 + yy, a.ny, per));
         roff[i] = (r < RING) ? yy * SX + xx : -1;
     }
 
@@ -239,7 +247,7 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
 
     for (int k = 0; k <= nplanes + 1; ++k, ++kbuf) {
         const int zk = zc0 - 1 + k;
-        const float cz = axis_coord(bc_index(zk, a.nz, per), a.nz, m1p1);
+        const float cz = __ldg(a.czs + bc_index(zk, a.nz, per));
         float* pl = buf + (kbuf & (NB - 1)) * PLANE;
         const bool halo_plane = (k == 0) || (k == nplanes + 1);
         float dTn[P][4];
