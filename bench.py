@@ -38,6 +38,19 @@ def flops_per_point(H: int) -> int:
     return 51 * H + 68
 
 
+def ncu_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the committed
+    `ncu --set full` capture of this same command (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_fused_default_summary.json")) as fh:
+            d = json.load(fh)[0]
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+        return float(rd[0]) * unit[rd[1]] + float(wr[0]) * unit[wr[1]]
+    except Exception:
+        return None
+
+
 def strict_fp32_peak():
     """Measured FMUL+FADD (non-contracted) pipe peak of this pool's B200, TFLOP/s, and where it came from."""
     p = os.path.join(ROOT, "profiles", "r01_microbench_fp32_long.json")
@@ -354,7 +367,7 @@ def main():
                     "loss": [float(e2e_out[0]), float(e2e_out[1])]},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32-pipe", "achieved": achieved, "peak": peak_strict, "unit": "TFLOP/s",
-                         "frac": achieved / peak_strict, "traffic": None,
+                         "frac": achieved / peak_strict, "traffic": ncu_dram_traffic() if (H == 64 and n == 256 and world == 1) else None,
                          "peak_source": peak_src, "peak_ffma": peak_ffma,
                          "flops_per_point": flops_per_point(H), "kernel_ms_mean": k_mean, "kernel_ms_min": k_min,
                          "note": "algorithmic flops (51H+68)/point x slab points / CUDA-event kernel time; peak = measured "
