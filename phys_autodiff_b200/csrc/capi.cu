@@ -233,11 +233,11 @@ struct FusedGeom {
     size_t smem;
 };
 
-template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED>
+template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR = false>
 int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool xchg, double* acc,
                    float* const R[4], cudaStream_t st) {
     constexpr int TX = 32, TY = TYB * P;
-    auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB, PACKED>;
+    auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB, PACKED, SPLITBAR>;
     const size_t smem = size_t(4) * 4 * (TX + 2) * (TY + 2) * sizeof(float);
     // per-kernel launch facts, queried once per process (this sits on the per-step host path)
     static int per_sm = 0;
@@ -281,17 +281,17 @@ int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
 template <int H>
 int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool dt, double* acc,
                    float* const R[4], cudaStream_t st) {
-    // <H, P columns/thread, warps/block, unroll (pairs of hidden units), min blocks/SM, packed>
+    // <H, P columns/thread, warps/block, unroll (pairs of hidden units), min blocks/SM, packed, split barrier>
     switch (c->fused_variant) {
         default:
-        case 0: return launch_fused_t<H, 4, 8, 2, 2, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x32, 2 x 256 threads/SM
-        case 1: return launch_fused_t<H, 4, 16, 2, 1, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x64, 1 x 512 threads/SM
-        case 2: return launch_fused_t<H, 4, 16, 1, 1, true>(c, g, s, tc, dt, acc, R, st);
-        case 3: return launch_fused_t<H, 4, 8, 2, 1, false>(c, g, s, tc, dt, acc, R, st);   // scalar FMUL/FADD cross-check
-        case 4: return launch_fused_t<H, 2, 16, 4, 1, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x32, 1 x 512
-        case 5: return launch_fused_t<H, 1, 8, 4, 4, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x8
-        case 6: return launch_fused_t<H, 2, 8, 2, 3, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x16, 3 x 256
-        case 7: return launch_fused_t<H, 4, 8, 1, 2, true>(c, g, s, tc, dt, acc, R, st);
+        case 0: return launch_fused_t<H, 4, 16, 2, 1, true, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x64, 1 x 512 threads/SM
+        case 1: return launch_fused_t<H, 4, 8, 2, 2, true, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x32, 2 x 256 threads/SM
+        case 2: return launch_fused_t<H, 4, 16, 2, 1, true, false>(c, g, s, tc, dt, acc, R, st);  // variant 0 with __syncthreads
+        case 3: return launch_fused_t<H, 4, 8, 2, 1, false, false>(c, g, s, tc, dt, acc, R, st);  // scalar FMUL/FADD cross-check
+        case 4: return launch_fused_t<H, 2, 16, 4, 1, true, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x32, 1 x 512
+        case 5: return launch_fused_t<H, 1, 8, 4, 4, true, false>(c, g, s, tc, dt, acc, R, st);   // tile 32x8
+        case 6: return launch_fused_t<H, 2, 8, 2, 3, true, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x16, 3 x 256
+        case 7: return launch_fused_t<H, 4, 8, 2, 2, true, false>(c, g, s, tc, dt, acc, R, st);   // variant 1 with __syncthreads
     }
 }
 

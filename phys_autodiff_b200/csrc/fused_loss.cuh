@@ -181,7 +181,23 @@ __global__ void k_xchg_only(const XchgArgs x, double* out) {
     if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
 }
 
-template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED>
+// ---- split-phase block barrier (mbarrier): arrive now, wait one plane later ----------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR = false>
 __global__ void __launch_bounds__(32 * TYB, MINB)
 k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) {
     constexpr int TX = 32, TY = TYB * P, NWARPS = TYB;
@@ -191,6 +207,15 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
     float* buf = smem;  // [NB][4][SY][SX]
     __shared__ double2 s_red[NWARPS];
     __shared__ unsigned int s_flag;
+    // SPLITBAR: two mbarriers used alternately by plane parity.  A warp ARRIVES after writing plane k and
+    // only WAITS for plane k-1's barrier (armed a whole plane earlier, so practically never blocking)
+    // before it reads plane k-1's neighbours: the ring-duty warps no longer hold the block up.  With four
+    // plane buffers a warp can never overwrite data a slower warp still reads (it cannot be two waits ahead).
+    __shared__ unsigned long long s_bar[2];
+    if (SPLITBAR) {
+        if (threadIdx.x == 0) { mbar_init(&s_bar[0], NWARPS); mbar_init(&s_bar[1], NWARPS); }
+        __syncthreads();
+    }
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // warp id == ty
     const bool per = a.periodic != 0;
@@ -286,7 +311,13 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
                 }
             }
         }
-        __syncthreads();
+        if (SPLITBAR) {
+            __syncwarp();
+            if (tx == 0) mbar_arrive(&s_bar[kbuf & 1]);
+            if (kbuf >= 1) mbar_wait(&s_bar[(kbuf - 1) & 1], unsigned((kbuf - 1) >> 1) & 1u);
+        } else {
+            __syncthreads();
+        }
         if (k >= 2) {
             // residual of plane zk-1: centre/x/y neighbours from plane buffer k-1, z neighbours from k-2 and k
             const float* pc = buf + ((kbuf - 1) & (NB - 1)) * PLANE;
@@ -322,8 +353,9 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
 #pragma unroll
             for (int c = 0; c < 4; ++c) dT[j][c] = dTn[j][c];
     }
-    // The next segment starts writing plane buffers that the slowest warp may still be reading.
-    __syncthreads();
+    // The next segment starts writing plane buffers that the slowest warp may still be reading
+    // (SPLITBAR keeps the one-plane lag across segments, so it needs nothing here).
+    if (!SPLITBAR) __syncthreads();
   }
     grid_reduce2<NWARPS>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag, &a.x);
 }
