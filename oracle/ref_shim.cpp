@@ -148,7 +148,7 @@ int ref_fused_loss_mt(const CGrid* g, int In, int H, int Out, int norm_m1p1, con
     for (int s = 0; s < 3; ++s) {
         std::vector<float> coords;
         phys::make_grid_coords(spec, ts[s], cfg.norm, coords);
-        const std::size_t chunk = 1 << 14;
+        const std::size_t chunk = 1 << 11;  // 2*chunk*H floats of reference scratch stay cache-resident
         const std::size_t nchunks = (N + chunk - 1) / chunk;
         auto work = [&](int tid) {
             std::vector<float> y(chunk * 4);

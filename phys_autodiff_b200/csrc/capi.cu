@@ -37,6 +37,7 @@ struct physad_ctx {
     cudaStream_t stream = nullptr;  // used by the *_host entry points
     physad_mlp_config cfg{4, 0, 4, 1};
     bool has_weights = false;
+    bool dev_weights_stale = true;
     std::vector<float> W1, b1, W2, b2;                             // host copy (feeds the parameter block)
     float *dW1 = nullptr, *db1 = nullptr, *dW2 = nullptr, *db2 = nullptr;  // device copy (generic MLP kernels)
     size_t dW_cap[4] = {0, 0, 0, 0};
@@ -468,27 +469,39 @@ int physad_set_weights(physad_ctx* c, const physad_mlp_config* cfg, const float*
     if (!c || !cfg || !W1 || !b1 || !W2 || !b2) return fail(PHYSAD_E_INVALID, "set_weights: null argument");
     if (cfg->In <= 0 || cfg->H <= 0 || cfg->Out <= 0) return fail(PHYSAD_E_INVALID, "set_weights: dims must be positive");
     if (cfg->norm != 0 && cfg->norm != 1) return fail(PHYSAD_E_INVALID, "set_weights: norm must be 0 or 1");
-    DeviceGuard dg(c->device);
     c->cfg = *cfg;
     const size_t n[4] = {size_t(cfg->H) * cfg->In, size_t(cfg->H), size_t(cfg->Out) * cfg->H, size_t(cfg->Out)};
     const float* src[4] = {W1, b1, W2, b2};
     std::vector<float>* host[4] = {&c->W1, &c->b1, &c->W2, &c->b2};
-    float** dev[4] = {&c->dW1, &c->db1, &c->dW2, &c->db2};
-    for (int k = 0; k < 4; ++k) {
-        host[k]->assign(src[k], src[k] + n[k]);
-        if (n[k] > c->dW_cap[k]) {
-            if (*dev[k]) CU(cudaFree(*dev[k]));
-            *dev[k] = nullptr;
-            CU(cudaMalloc(dev[k], n[k] * sizeof(float)));
-            c->dW_cap[k] = n[k];
-        }
-        // host vector is owned by the context and outlives the copy
-        CU(cudaMemcpyAsync(*dev[k], host[k]->data(), n[k] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    }
-    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; ++k) host[k]->assign(src[k], src[k] + n[k]);
+    // The grid / fused kernels take the weights through the kernel-parameter block built from this host
+    // copy at launch; the device copy is only needed by the explicit-coordinate MLP kernels and is
+    // refreshed lazily there.
+    c->dev_weights_stale = true;
     c->has_weights = true;
     return 0;
 }
+
+namespace {
+int upload_weights_if_stale(physad_ctx* c, cudaStream_t st) {
+    if (!c->dev_weights_stale) return 0;
+    std::vector<float>* host[4] = {&c->W1, &c->b1, &c->W2, &c->b2};
+    float** dev[4] = {&c->dW1, &c->db1, &c->dW2, &c->db2};
+    for (int k = 0; k < 4; ++k) {
+        const size_t n = host[k]->size();
+        if (n > c->dW_cap[k]) {
+            if (*dev[k]) CU(cudaFree(*dev[k]));
+            *dev[k] = nullptr;
+            CU(cudaMalloc(dev[k], n * sizeof(float)));
+            c->dW_cap[k] = n;
+        }
+        // pageable source: the copy is staged before the call returns, so the host vector may change afterwards
+        CU(cudaMemcpyAsync(*dev[k], host[k]->data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    c->dev_weights_stale = false;
+    return 0;
+}
+}  // namespace
 
 // ---- MLP operator -----------------------------------------------------------------------------
 int physad_mlp_forward_dev(physad_ctx* c, const float* x, float* y, size_t B, void* stream) {
@@ -497,6 +510,7 @@ int physad_mlp_forward_dev(physad_ctx* c, const float* x, float* y, size_t B, vo
     if (B == 0) return 0;
     DeviceGuard dg(c->device);
     cudaStream_t st = cudaStream_t(stream);
+    if (int rc = upload_weights_if_stale(c, st)) return rc;
     const int In = c->cfg.In, H = c->cfg.H, Out = c->cfg.Out;
     const size_t smem4 = size_t(H) * (2 * sizeof(float4) + sizeof(float));
     if (In == 4 && Out == 4 && smem4 <= 200 * 1024 && (uintptr_t(x) % 16 == 0) && (uintptr_t(y) % 16 == 0)) {

@@ -208,6 +208,15 @@ class Context:
             return acc
         return launch
 
+    def _read_acc(self, acc):
+        """16-byte device -> pinned host read of the two sums, then a stream sync."""
+        import torch
+        if getattr(self, "_pinned_acc", None) is None:
+            self._pinned_acc = torch.empty(2, dtype=torch.float64).pin_memory()
+        self._pinned_acc.copy_(acc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pinned_acc.numpy()
+
     def finalize(self, acc, pw: PhysWeights, n_global: int):
         a = (C.c_double * 2)(float(acc[0]), float(acc[1]))
         ls, lu = C.c_float(), C.c_float()
@@ -231,7 +240,7 @@ class Context:
             acc = self.fused_loss_acc(g, t, dt, slab=slab, residuals=R)
             if world > 1:
                 dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
-        ls, lu = self.finalize(acc.cpu().numpy(), pw, g.N)
+        ls, lu = self.finalize(self._read_acc(acc), pw, g.N)
         return (ls, lu, tuple(R)) if want_residuals else (ls, lu)
 
     # -- host-buffer forms (the reference's contract) -----------------------------------------------------
