@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--ref-planes", type=int, default=32, help="z planes per step of the reference arm")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: in-kernel peer-memory all-reduce (default) or kernel + NCCL all-reduce")
+    ap.add_argument("--emulate-rank-of", type=int, default=0,
+                    help="tuning aid: time only the kernel for rank 0's slab of an N-rank run on ONE GPU and exit")
+    ap.add_argument("--emulate-planes", type=int, default=0, help="with --emulate-rank-of: slab = first P planes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="skip the NVML clock sampler thread (diagnostics)")
     ap.add_argument("--extra", action="store_true", help="also time H=32 and H=128 (reported under 'extra')")
@@ -239,6 +242,20 @@ def main():
     ctx.set_weights(cfg, *w)
     slab = slab_for_rank(n, rank, world)
     acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    if args.emulate_rank_of > 1:
+        slab = slab_for_rank(n, 0, args.emulate_rank_of)
+        if args.emulate_planes > 0:
+            slab = (0, args.emulate_planes)
+        ts = []
+        for i in range(args.steps + 5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ctx.fused_loss_acc(g, T0, DT, slab=slab, acc=acc); e1.record(); e1.synchronize()
+            if i >= 5:
+                ts.append(e0.elapsed_time(e1))
+        print(json.dumps({"emulate_rank_of": args.emulate_rank_of, "slab": slab, "variant": args.variant,
+                          "kernel_ms_mean": statistics.mean(ts), "kernel_ms_min": min(ts),
+                          "ideal_ms_if_perfect_scaling": None}))
+        return
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():

@@ -356,15 +356,22 @@ int launch_grid(physad_ctx* c, const physad_grid* g, const physad_slab& s, const
 // ---- physics on supplied fields --------------------------------------------------------------
 template <bool WRITE_R, bool REDUCE, bool SCALE>
 int launch_phys(physad_ctx* c, const physad_grid* g, PhysArgs a, cudaStream_t st) {
-    const size_t N = size_t(g->nx) * g->ny * g->nz;
-    const size_t blocks = (N + 255) / 256;
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.periodic = g->periodic != 0;
     a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
+    // 32 x 8 column tiles, each marching a z chunk; enough chunks for ~16 blocks per SM
+    const unsigned tx = unsigned((g->nx + 31) / 32), ty = unsigned((g->ny + 7) / 8);
+    if (ty > 65535u) return fail(PHYSAD_E_UNSUPPORTED, "phys kernels: ny > 524280");
+    const long long want = (long long)c->sm_count * 16;
+    long long nch = std::max(1LL, std::min<long long>(g->nz, (want + (long long)tx * ty - 1) / ((long long)tx * ty)));
+    a.zc = int((g->nz + nch - 1) / nch);
+    nch = (g->nz + a.zc - 1) / a.zc;
+    if (nch > 65535) { a.zc = (g->nz + 65534) / 65535; nch = (g->nz + a.zc - 1) / a.zc; }
+    const dim3 grid(tx, ty, unsigned(nch));
     if (REDUCE) {
-        if (int rc = ensure_partials(c, blocks)) return rc;
+        if (int rc = ensure_partials(c, size_t(tx) * ty * nch)) return rc;
         a.partials = c->partials; a.ticket = c->ticket;
     }
-    k_phys_residual<WRITE_R, REDUCE, SCALE><<<unsigned(blocks), 256, 0, st>>>(a);
+    k_phys_residual<WRITE_R, REDUCE, SCALE><<<grid, 256, 0, st>>>(a);
     c->launches++;
     CU(cudaGetLastError());
     return 0;

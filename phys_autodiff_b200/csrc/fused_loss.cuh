@@ -131,8 +131,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Block-wide {a,b} sum -> per-block partial -> grid total written by the last block to finish.
 template <int NWARPS>
-__device__ __forceinline__ void grid_reduce2(double a, double b, double2* partials, unsigned int* ticket, double* out,
-                                             double2* s_red, unsigned int* s_flag, const XchgArgs* x = nullptr) {
+__device__ __forceinline__ void grid_reduce2_lin(double a, double b, double2* partials, unsigned int* ticket, double* out,
+                                                 double2* s_red, unsigned int* s_flag, unsigned int block_lin,
+                                                 unsigned int nblocks, const XchgArgs* x = nullptr) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     a = warp_sum(a);
     b = warp_sum(b);
@@ -142,16 +143,16 @@ __device__ __forceinline__ void grid_reduce2(double a, double b, double2* partia
         double sa = 0.0, sb = 0.0;
 #pragma unroll
         for (int i = 0; i < NWARPS; ++i) { sa += s_red[i].x; sb += s_red[i].y; }
-        partials[blockIdx.x] = make_double2(sa, sb);
+        partials[block_lin] = make_double2(sa, sb);
         __threadfence();
         *s_flag = atomicAdd(ticket, 1u);
     }
     __syncthreads();
-    if (*s_flag != gridDim.x - 1) return;
+    if (*s_flag != nblocks - 1) return;
     // last block: fixed-order strided sums, then the same tree
     __threadfence();
     double sa = 0.0, sb = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += NWARPS * 32) {
+    for (unsigned int i = threadIdx.x; i < nblocks; i += NWARPS * 32) {
         const double2 p = __ldcg(&partials[i]);
         sa += p.x; sb += p.y;
     }
@@ -171,6 +172,12 @@ __device__ __forceinline__ void grid_reduce2(double a, double b, double2* partia
             *ticket = 0u;
         }
     }
+}
+
+template <int NWARPS>
+__device__ __forceinline__ void grid_reduce2(double a, double b, double2* partials, unsigned int* ticket, double* out,
+                                             double2* s_red, unsigned int* s_flag, const XchgArgs* x = nullptr) {
+    grid_reduce2_lin<NWARPS>(a, b, partials, ticket, out, s_red, s_flag, blockIdx.x, gridDim.x, x);
 }
 
 // Exchange-only launch for a rank whose slab is empty (more ranks than planes): it still has to

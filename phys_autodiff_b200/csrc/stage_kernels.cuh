@@ -123,16 +123,23 @@ __global__ void __launch_bounds__(256) k_mlp_generic_out(const float* __restrict
 
 // ---------------------------------------------------------------------------------------------
 // Physics residual on supplied fields (reference src/phys_cpu.cpp:25-110; fp32 like the reference's
-// CUDA kernels).  One thread per point; the 7-point cross is read through L1/L2 (x+-1 share the
-// centre's lines, y+-1 / z+-1 are L2 hits), so HBM sees each field once: 48 B in + 16 B out per point.
+// CUDA kernels).  HBM-bound: 48 B in + 16 B out per point, everything else must stay out of the way.
+//   * a block owns a 32 x 8 (x,y) tile and MARCHES over a chunk of z planes: the time-t values of
+//     planes z-1, z, z+1 roll through registers, so z neighbours cost no loads; x/y neighbours are L1
+//     hits on lines the block's own centre loads brought in (a warp is one 128-byte row segment);
+//   * indices come from the 3-D launch geometry (no integer division per point), wrap/clamp of a +-1
+//     offset is two compares;
+//   * REDUCE accumulates the squares per thread in double over the whole march, so the double
+//     shuffles / ticket of grid_reduce2 run once per block, not once per 256 points.
 //   WRITE_R : store the four residual arrays
-//   REDUCE  : accumulate {sum Rs^2, sum |Ru|^2} in double -> acc_out (on-device loss reduction)
+//   REDUCE  : {sum Rs^2, sum |Ru|^2} in double -> acc_out (on-device loss reduction)
 //   SCALE   : store scale_s*Rs, scale_u*Ru instead of R (backward recomputed from fields,
 //             cuda_phys_loss_backward_fused, include/phys.h:132-143)
 // ---------------------------------------------------------------------------------------------
 struct PhysArgs {
     int nx, ny, nz;
     int periodic;
+    int zc;  // planes per z chunk
     float inv2dt, inv2hx, inv2hy, inv2hz;
     float scale_s, scale_u;
     const float* s_m; const float* s_0; const float* s_p;
@@ -141,50 +148,67 @@ struct PhysArgs {
     double2* partials; unsigned int* ticket; double* acc_out;
 };
 
+// neighbour index for an offset of +-1 (n >= 1): wrap or clamp without a division
+__device__ __forceinline__ int nb1(int v, int n, bool periodic) {
+    if (periodic) return v < 0 ? v + n : (v >= n ? v - n : v);
+    return v < 0 ? 0 : (v >= n ? n - 1 : v);
+}
+
 template <bool WRITE_R, bool REDUCE, bool SCALE>
 __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
     __shared__ double2 s_red[8];
     __shared__ unsigned int s_flag;
-    const size_t N = size_t(a.nx) * a.ny * a.nz;
-    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool per = a.periodic != 0;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int z0 = blockIdx.z * a.zc, z1 = min(a.nz, z0 + a.zc);
+    const size_t N = size_t(a.nx) * a.ny * a.nz, pln = size_t(a.nx) * a.ny;
     double acc_s = 0.0, acc_u = 0.0;
-    if (i < N) {
-        const bool per = a.periodic != 0;
-        const int x = int(i % a.nx);
-        const size_t r = i / a.nx;
-        const int y = int(r % a.ny), z = int(r / a.ny);
-        const size_t row = size_t(a.nx), pln = size_t(a.nx) * a.ny;
-        const size_t ixp = i - x + bc_index(x + 1, a.nx, per), ixm = i - x + bc_index(x - 1, a.nx, per);
-        const size_t iyp = i + (ptrdiff_t(bc_index(y + 1, a.ny, per)) - y) * ptrdiff_t(row);
-        const size_t iym = i + (ptrdiff_t(bc_index(y - 1, a.ny, per)) - y) * ptrdiff_t(row);
-        const size_t izp = i + (ptrdiff_t(bc_index(z + 1, a.nz, per)) - z) * ptrdiff_t(pln);
-        const size_t izm = i + (ptrdiff_t(bc_index(z - 1, a.nz, per)) - z) * ptrdiff_t(pln);
-        float f[4], dT[4], gx[4], gy[4], gz[4], R[4];
+    if (x < a.nx && y < a.ny) {
+        const size_t row = size_t(y) * a.nx;
+        const size_t oc = row + x, oxm = row + nb1(x - 1, a.nx, per), oxp = row + nb1(x + 1, a.nx, per);
+        const size_t oym = size_t(nb1(y - 1, a.ny, per)) * a.nx + x, oyp = size_t(nb1(y + 1, a.ny, per)) * a.nx + x;
+        const float* f0[4] = {a.s_0, a.u_0, a.u_0 + N, a.u_0 + 2 * N};
+        const float* fm[4] = {a.s_m, a.u_m, a.u_m + N, a.u_m + 2 * N};
+        const float* fp[4] = {a.s_p, a.u_p, a.u_p + N, a.u_p + 2 * N};
+        float lo[4], mid[4], hi[4];  // time-t values at z-1, z, z+1 of this column
+        {
+            const size_t pm = size_t(nb1(z0 - 1, a.nz, per)) * pln + oc, pc = size_t(z0) * pln + oc;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float* q0 = c == 0 ? a.s_0 : a.u_0 + size_t(c - 1) * N;
-            const float* qm = c == 0 ? a.s_m : a.u_m + size_t(c - 1) * N;
-            const float* qp = c == 0 ? a.s_p : a.u_p + size_t(c - 1) * N;
-            f[c] = __ldg(q0 + i);
-            dT[c] = central_diff(__ldg(qp + i), __ldg(qm + i), a.inv2dt);
-            gx[c] = central_diff(__ldg(q0 + ixp), __ldg(q0 + ixm), a.inv2hx);
-            gy[c] = central_diff(__ldg(q0 + iyp), __ldg(q0 + iym), a.inv2hy);
-            gz[c] = central_diff(__ldg(q0 + izp), __ldg(q0 + izm), a.inv2hz);
+            for (int c = 0; c < 4; ++c) { lo[c] = __ldg(f0[c] + pm); mid[c] = __ldg(f0[c] + pc); }
         }
-        point_residual(f, gx, gy, gz, dT, R);
-        const float Rs = R[0], Rx = R[1], Ry = R[2], Rz = R[3];
-        if (WRITE_R) {
-            if (a.R[0]) a.R[0][i] = SCALE ? a.scale_s * Rs : Rs;
-            if (a.R[1]) a.R[1][i] = SCALE ? a.scale_u * Rx : Rx;
-            if (a.R[2]) a.R[2][i] = SCALE ? a.scale_u * Ry : Ry;
-            if (a.R[3]) a.R[3][i] = SCALE ? a.scale_u * Rz : Rz;
-        }
-        if (REDUCE) {
-            acc_s = double(Rs) * double(Rs);
-            acc_u = double(Rx) * double(Rx) + double(Ry) * double(Ry) + double(Rz) * double(Rz);
+        for (int z = z0; z < z1; ++z) {
+            const size_t pz = size_t(z) * pln, pzp = size_t(nb1(z + 1, a.nz, per)) * pln;
+            float dT[4], gx[4], gy[4], gz[4], R[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                hi[c] = __ldg(f0[c] + pzp + oc);
+                dT[c] = central_diff(__ldg(fp[c] + pz + oc), __ldg(fm[c] + pz + oc), a.inv2dt);
+                gx[c] = central_diff(__ldg(f0[c] + pz + oxp), __ldg(f0[c] + pz + oxm), a.inv2hx);
+                gy[c] = central_diff(__ldg(f0[c] + pz + oyp), __ldg(f0[c] + pz + oym), a.inv2hy);
+                gz[c] = central_diff(hi[c], lo[c], a.inv2hz);
+            }
+            point_residual(mid, gx, gy, gz, dT, R);
+            if (WRITE_R) {
+                const size_t i = pz + oc;
+                if (a.R[0]) a.R[0][i] = SCALE ? a.scale_s * R[0] : R[0];
+                if (a.R[1]) a.R[1][i] = SCALE ? a.scale_u * R[1] : R[1];
+                if (a.R[2]) a.R[2][i] = SCALE ? a.scale_u * R[2] : R[2];
+                if (a.R[3]) a.R[3][i] = SCALE ? a.scale_u * R[3] : R[3];
+            }
+            if (REDUCE) {
+                acc_s += double(R[0]) * double(R[0]);
+                acc_u += double(R[1]) * double(R[1]) + double(R[2]) * double(R[2]) + double(R[3]) * double(R[3]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { lo[c] = mid[c]; mid[c] = hi[c]; }
         }
     }
-    if (REDUCE) grid_reduce2<8>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag);
+    if (REDUCE) {
+        // grid_reduce2 indexes partials by a linear block id
+        const unsigned int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const unsigned int nblk = gridDim.x * gridDim.y * gridDim.z;
+        grid_reduce2_lin<8>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag, lin, nblk);
+    }
 }
 
 // g = scale * R (reference src/phys_cpu.cpp:151-170); four arrays in one launch, float4-vectorised
