@@ -192,6 +192,13 @@ void physad_finalize_loss(const double acc[2], const physad_phys_weights* w, siz
 void physad_mlp_random_init(int In, int H, int Out, unsigned int seed, float scale, float* W1, float* b1, float* W2,
                             float* b2);
 
+/* Host-only: the work partition the fused kernel is launched with.  The sequence of tiles x planes
+ * tile-planes (tile-major) is cut into at most `slots` contiguous ranges of equal cost, a range paying
+ * ~0.9 plane-equivalents for every z-segment it starts (its recomputed halo planes).  Writes the
+ * range boundaries (first = 0, last = tiles*planes) to out and returns their count (blocks + 1), or a
+ * negative status.  Exposed so the partition can be tested without a GPU. */
+int physad_plan_ranges(int tiles, int planes, int slots, int* out, int out_cap);
+
 /* Tuning knob for experiments: selects the fused-kernel variant (0 = default). Returns the previous value. */
 int physad_set_fused_variant(physad_ctx* ctx, int variant);
 /* Number of kernel launches this context has enqueued since creation (bench.py's gpu_launches). */

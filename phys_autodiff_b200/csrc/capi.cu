@@ -236,7 +236,7 @@ struct FusedGeom {
 
 template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR = false>
 int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool xchg, double* acc,
-                   float* const R[4], cudaStream_t st) {
+                   float* const R[4], cudaStream_t st, int blocks_per_sm_cap = 0) {
     constexpr int TX = 32, TY = TYB * P;
     auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB, PACKED, SPLITBAR>;
     const size_t smem = size_t(4) * 4 * (TX + 2) * (TY + 2) * sizeof(float);
@@ -254,7 +254,8 @@ int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
     }
     const int tiles_x = (g->nx + TX - 1) / TX, tiles_y = (g->ny + TY - 1) / TY;
     // persistent grid: one block per resident slot, each owning an equal-cost share of the tile-planes
-    const long long slots = env_blocks > 0 ? env_blocks : (long long)per_sm * c->sm_count;
+    const int bps = blocks_per_sm_cap > 0 ? std::min(per_sm, blocks_per_sm_cap) : per_sm;
+    const long long slots = env_blocks > 0 ? env_blocks : (long long)bps * c->sm_count;
     if (int rc = build_fused_plan(c, g, s, TX, TY, slots, st)) return rc;
     const long long blocks = c->plan.blocks;
     FusedArgs a{};
@@ -285,7 +286,15 @@ int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
     // <H, P columns/thread, warps/block, unroll (pairs of hidden units), min blocks/SM, packed, split barrier>
     switch (c->fused_variant) {
         default:
-        case 0: return launch_fused_t<H, 4, 16, 2, 1, true, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x64, 1 x 512 threads/SM
+        case 0: {
+            // Small slabs (multi-GPU strong scaling): a block's share is only a few planes, and every z-segment
+            // costs ~1.15 plane-steps of halo + prologue.  Halving the columns in flight per SM (one 256-thread
+            // block) doubles the segment length; measured 0.1765 vs 0.1866 ms for a 256x256x32 slab.
+            const long long tile_planes = (long long)((g->nx + 31) / 32) * ((g->ny + 63) / 64) * (s.z_end - s.z_begin);
+            if (tile_planes < 12LL * c->sm_count)
+                return launch_fused_t<H, 4, 8, 2, 2, true, true>(c, g, s, tc, dt, acc, R, st, 1);
+            return launch_fused_t<H, 4, 16, 2, 1, true, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x64, 1 x 512 threads/SM
+        }
         case 1: return launch_fused_t<H, 4, 8, 2, 2, true, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x32, 2 x 256 threads/SM
         case 2: return launch_fused_t<H, 4, 16, 2, 1, true, false>(c, g, s, tc, dt, acc, R, st);  // variant 0 with __syncthreads
         case 3: return launch_fused_t<H, 4, 8, 2, 1, false, false>(c, g, s, tc, dt, acc, R, st);  // scalar FMUL/FADD cross-check
@@ -823,6 +832,14 @@ int physad_fused_loss_allreduce_dev(physad_ctx* c, const physad_grid* g, const p
     DeviceGuard dg(c->device);
     float* R[4] = {Rs, Rx, Ry, Rz};
     return launch_fused(c, g, s, t, dt, acc, R, cudaStream_t(stream), true);
+}
+
+int physad_plan_ranges(int tiles, int planes, int slots, int* out, int out_cap) {
+    if (tiles < 1 || planes < 1 || slots < 1 || !out) return fail(PHYSAD_E_INVALID, "plan_ranges: bad argument");
+    const std::vector<int> r = balanced_ranges(tiles, planes, std::min<long long>(slots, (long long)tiles * planes), 0.9);
+    if (int(r.size()) > out_cap) return fail(PHYSAD_E_INVALID, "plan_ranges: output too small");
+    std::copy(r.begin(), r.end(), out);
+    return int(r.size());
 }
 
 int physad_xchg_export(physad_ctx* c, void* handle_out) {

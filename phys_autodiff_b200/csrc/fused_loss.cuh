@@ -208,6 +208,7 @@ template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBA
 __global__ void __launch_bounds__(32 * TYB, MINB)
 k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) {
     constexpr int TX = 32, TY = TYB * P, NWARPS = TYB;
+    static_assert((NWARPS & (NWARPS - 1)) == 0, "warps per block must be a power of two");
     constexpr int SX = TX + 2, SY = TY + 2, CH = SX * SY, PLANE = 4 * CH, NB = 4;
     constexpr int RING = 2 * TX + 2 * TY, NTASK = (RING + 31) / 32;
     extern __shared__ float smem[];
@@ -254,23 +255,6 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
         cy[j] = __ldg(a.cys + bc_index(gy, a.ny, per));
         live[j] = gx < a.nx && gy < a.ny;
     }
-    // this lane's ring columns (one per task), fixed for the whole march
-    float rcx[NTASK], rcy[NTASK];
-    int roff[NTASK];
-#pragma unroll
-    for (int i = 0; i < NTASK; ++i) {
-        const int r = i * 32 + tx;
-        int xx, yy;
-        if (r < TX) { xx = 1 + r; yy = 0; }
-        else if (r < 2 * TX) { xx = 1 + r - TX; yy = SY - 1; }
-        else if (r < 2 * TX + TY) { xx = 0; yy = 1 + r - 2 * TX; }
-        else { xx = SX - 1; yy = 1 + r - 2 * TX - TY; }
-        if (r >= RING) { xx = 0; yy = 0; }  // idle lane of the last task: harmless duplicate slot
-        rcx[i] = __ldg(a.cxs + bc_index(x0 - 1 + xx, a.nx, per));
-        rcy[i] = __ldg(a.cys + bc_index(y0 - 1 + yy, a.ny, per));
-        roff[i] = (r < RING) ? yy * SX + xx : -1;
-    }
-
     float dT[P][4];  // time derivative of the plane whose residual is pending
 #pragma unroll
     for (int j = 0; j < P; ++j)
@@ -304,16 +288,28 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
                     dTn[j][c] = central_diff(y[j][2][c], y[j][0][c], a.inv2dt);
                 }
             }
-            // ring duty for this plane (x/y neighbours of the tile edge), rotating over warps
-#pragma unroll
-            for (int i = 0; i < NTASK; ++i) {
-                if ((i + kbuf) % NWARPS == ty) {
+            // ring duty for this plane (x/y neighbours of the tile edge): NTASK tasks of 32 ring columns,
+            // task i goes to warp (i + kbuf) % NWARPS, i.e. this warp has at most one task per plane and the
+            // duty rotates over the warps from plane to plane.  Ring slot -> coordinates are recomputed here
+            // (two cached table loads) instead of living in registers for the whole march.
+            {
+                static_assert(NTASK <= NWARPS, "one ring task per warp and plane");
+                const int i = (ty - kbuf) & (NWARPS - 1);
+                if (i < NTASK) {
+                    const int r = i * 32 + tx;
+                    int xx, yy;
+                    if (r < TX) { xx = 1 + r; yy = 0; }
+                    else if (r < 2 * TX) { xx = 1 + r - TX; yy = SY - 1; }
+                    else if (r < 2 * TX + TY) { xx = 0; yy = 1 + r - 2 * TX; }
+                    else { xx = SX - 1; yy = 1 + r - 2 * TX - TY; }
+                    if (r >= RING) { xx = 0; yy = 0; }  // idle lanes of the last task compute a throw-away column
+                    const float rcx = __ldg(a.cxs + bc_index(x0 - 1 + xx, a.nx, per));
+                    const float rc[1] = {__ldg(a.cys + bc_index(y0 - 1 + yy, a.ny, per))};
                     float yr[1][1][4];
-                    const float rc[1] = {rcy[i]};
-                    mlp_eval<H, 1, 1, UNROLL, PACKED>(w, rcx[i], rc, cz, yr);
-                    if (roff[i] >= 0) {
+                    mlp_eval<H, 1, 1, UNROLL, PACKED>(w, rcx, rc, cz, yr);
+                    if (r < RING) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) pl[c * CH + roff[i]] = yr[0][0][c];
+                        for (int c = 0; c < 4; ++c) pl[c * CH + yy * SX + xx] = yr[0][0][c];
                     }
                 }
             }

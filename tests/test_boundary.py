@@ -137,3 +137,24 @@ def test_strict_kernels_have_no_contracted_fma_in_mlp(libpath):
         # (__fdiv_rn, 9 each) in the grid kernels; a contracted MLP loop would add one per MAC
         limit = 27 if "k_mlp_grid" in k else 0
         assert v["FFMA"] <= limit and v["FFMA2"] == 0, (k, v)
+
+
+def test_fused_work_partition_properties(libpath):
+    """Host logic of the persistent launch (capi.cu: balanced_ranges): contiguous cover of the tile-plane
+    sequence, no more blocks than slots, and near-equal cost (planes + 0.9 per started z-segment)."""
+    lib = C.CDLL(libpath)
+    for tiles, planes, slots in [(32, 256, 148), (64, 256, 296), (32, 32, 148), (64, 32, 148), (4, 64, 296),
+                                 (1, 1, 148), (1, 5, 3), (7, 3, 2), (128, 16, 148), (3, 1000, 296)]:
+        out = (C.c_int * (slots + 2))()
+        n = lib.physad_plan_ranges(tiles, planes, slots, out, slots + 2)
+        assert n >= 2, (tiles, planes, slots, n)
+        r = list(out[:n])
+        assert r[0] == 0 and r[-1] == tiles * planes
+        assert all(b > a for a, b in zip(r, r[1:]))          # non-empty, increasing
+        assert n - 1 <= min(slots, tiles * planes)
+        costs = []
+        for a, b in zip(r, r[1:]):
+            segs = (b - 1) // planes - a // planes + 1        # tiles touched by [a, b)
+            costs.append((b - a) + 0.9 * segs)
+        ideal = (tiles * planes + 0.9 * max(tiles, n - 1)) / (n - 1)
+        assert max(costs) <= ideal + 2.9, (tiles, planes, slots, max(costs), ideal)  # one plane + one extra segment of slack
