@@ -6,8 +6,8 @@
 // x: B x In, y: B x Out (row-major, HOST pointers, caller-owned); W1: H x In, W2: Out x H row-major.
 // This library provides mlp_forward<ExecCuda> (bit-exact with the reference's
 // mlp_forward<ExecCpu>, src/mlp_cpu.cpp:14-36: fp32, separate multiply and add, k/h ascending).
-// mlp_backward<ExecCuda> (MSE weight gradients, src/mlp_cuda.cu:123-184) is a training op outside
-// the grid->loss hot path; the symbol exists so existing callers link, and aborts if called.
+// mlp_backward<ExecCuda> (MSE weight gradients of mean((y - y_target)^2), src/mlp_cuda.cu:123-184) is
+// provided bit-exact with mlp_backward<ExecCpu> as well; it is outside the grid->loss hot path and not tuned.
 #ifndef PHYS_AUTODIFF_MLP_H
 #define PHYS_AUTODIFF_MLP_H
 #include <cstddef>

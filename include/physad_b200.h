@@ -92,6 +92,16 @@ int physad_set_weights(physad_ctx* ctx, const physad_mlp_config* cfg, const floa
 int physad_mlp_forward_dev(physad_ctx* ctx, const float* x, float* y, size_t B, void* stream);
 int physad_mlp_forward_host(physad_ctx* ctx, const float* x, float* y, size_t B);
 
+/* MSE weight gradients of the same MLP: dW1[H*In], db1[H], dW2[Out*H], db2[Out] for inputs x[B*In]
+ * and targets y_target[B*Out], loss = mean((y - y_target)^2).  Replaces mlp_backward<ExecCuda>
+ * (include/mlp.h:8-9, src/mlp_cuda.cu:123-184).  Bit-exact with mlp_backward<ExecCpu>
+ * (src/mlp_cpu.cpp:38-85), which fixes the algorithm to a sequential fp32 walk over the batch per
+ * gradient entry (outside the grid->loss path, not tuned). */
+int physad_mlp_backward_dev(physad_ctx* ctx, const float* x, const float* y_target, float* dW1, float* db1, float* dW2,
+                            float* db2, size_t B, void* stream);
+int physad_mlp_backward_host(physad_ctx* ctx, const float* x, const float* y_target, float* dW1, float* db1,
+                             float* dW2, float* db2, size_t B);
+
 /* MLP over the grid at time t, coordinates generated from the point index (never materialised).
  * out: AoS [slab points][4].  Replaces mlp_grid_infer_cuda (include/mlp_grid.h:45,
  * src/mlp_grid.cpp:61-67).  Requires In = Out = 4. */

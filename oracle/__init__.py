@@ -96,6 +96,14 @@ class _Oracle:
         f(_fp(x), _fp(W1), _fp(b1), _fp(W2), _fp(b2), _fp(y), C.c_size_t(B), C.c_size_t(In), C.c_size_t(H), C.c_size_t(Out))
         return y
 
+    def mlp_backward(self, x, y_target, W1, b1, W2, b2, B, In, H, Out):
+        dW1 = np.empty(H * In, np.float32); db1 = np.empty(H, np.float32)
+        dW2 = np.empty(Out * H, np.float32); db2 = np.empty(Out, np.float32)
+        f = self._fn("mlp_backward" if self.kind == "port" else "mlp_backward_cpu"); f.restype = None
+        f(_fp(x), _fp(y_target), _fp(W1), _fp(b1), _fp(W2), _fp(b2), _fp(dW1), _fp(db1), _fp(dW2), _fp(db2),
+          C.c_size_t(B), C.c_size_t(In), C.c_size_t(H), C.c_size_t(Out))
+        return dW1, db1, dW2, db2
+
     def mlp_grid_infer(self, g: Grid, w, t: float, m1p1: bool = True) -> np.ndarray:
         W1, b1, W2, b2 = w
         H = b1.size

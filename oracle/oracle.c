@@ -135,6 +135,61 @@ void oracle_mlp_forward(const float* x, const float* W1, const float* b1, const 
     free(a);
 }
 
+/* MLP backward (MSE weight gradients), src/mlp_cpu.cpp:38-85: forward pass, gz2 = (2/float(B*Out))*(y - target),
+ * then every gradient entry accumulated sequentially over the batch in fp32 (i ascending), gz1 =
+ * (sum_o gz2[i,o]*W2[o,h]) * (z1 > 0). */
+void oracle_mlp_backward(const float* x, const float* y_target, const float* W1, const float* b1, const float* W2,
+                         const float* b2, float* dW1, float* db1, float* dW2, float* db2, size_t B, size_t In, size_t H,
+                         size_t Out) {
+    float* z1 = (float*)malloc(sizeof(float) * B * H);
+    float* a1 = (float*)malloc(sizeof(float) * B * H);
+    float* gz2 = (float*)malloc(sizeof(float) * B * Out);
+    float* gz1 = (float*)malloc(sizeof(float) * B * H);
+    for (size_t i = 0; i < B; ++i)
+        for (size_t h = 0; h < H; ++h) {
+            float s = b1[h];
+            for (size_t k = 0; k < In; ++k) s += W1[h * In + k] * x[i * In + k];
+            z1[i * H + h] = s;
+            a1[i * H + h] = s > 0.f ? s : 0.f;
+        }
+    const float scale = 2.f / (float)(B * Out);
+    for (size_t i = 0; i < B; ++i)
+        for (size_t o = 0; o < Out; ++o) {
+            float s = b2[o];
+            for (size_t h = 0; h < H; ++h) s += W2[o * H + h] * a1[i * H + h];
+            gz2[i * Out + o] = scale * (s - y_target[i * Out + o]);
+        }
+    for (size_t o = 0; o < Out; ++o)
+        for (size_t h = 0; h < H; ++h) {
+            float s = 0.f;
+            for (size_t i = 0; i < B; ++i) s += gz2[i * Out + o] * a1[i * H + h];
+            dW2[o * H + h] = s;
+        }
+    for (size_t o = 0; o < Out; ++o) {
+        float s = 0.f;
+        for (size_t i = 0; i < B; ++i) s += gz2[i * Out + o];
+        db2[o] = s;
+    }
+    for (size_t i = 0; i < B; ++i)
+        for (size_t h = 0; h < H; ++h) {
+            float s = 0.f;
+            for (size_t o = 0; o < Out; ++o) s += gz2[i * Out + o] * W2[o * H + h];
+            gz1[i * H + h] = s * (z1[i * H + h] > 0.f ? 1.f : 0.f);
+        }
+    for (size_t h = 0; h < H; ++h)
+        for (size_t k = 0; k < In; ++k) {
+            float s = 0.f;
+            for (size_t i = 0; i < B; ++i) s += gz1[i * H + h] * x[i * In + k];
+            dW1[h * In + k] = s;
+        }
+    for (size_t h = 0; h < H; ++h) {
+        float s = 0.f;
+        for (size_t i = 0; i < B; ++i) s += gz1[i * H + h];
+        db1[h] = s;
+    }
+    free(z1); free(a1); free(gz2); free(gz1);
+}
+
 /* MLP over the grid at time t -> AoS [sigma,ux,uy,uz] per point.  src/mlp_grid.cpp:53-59. */
 void oracle_mlp_grid_infer(const oracle_grid* g, int In, int H, int Out, int m1p1, const float* W1, const float* b1,
                            const float* W2, const float* b2, float t, float* out) {

@@ -23,6 +23,7 @@
 #include <vector>
 
 // src/mlp_grid.cpp:50 references mlp_forward<ExecCuda>; a CPU-only oracle must still link.
+// (mlp_backward<ExecCuda> is referenced by nothing in the three CPU sources.)
 template <>
 void mlp_forward<ExecCuda>(const float*, const float*, const float*, const float*, const float*, float*,
                            std::size_t, std::size_t, std::size_t, std::size_t) {
@@ -85,6 +86,12 @@ void ref_make_grid_coords(const CGrid* g, float t, int norm_m1p1, float* coords 
 void ref_mlp_forward_cpu(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* y,
                          size_t B, size_t In, size_t H, size_t Out) {
     mlp_forward<ExecCpu>(x, W1, b1, W2, b2, y, B, In, H, Out);
+}
+
+void ref_mlp_backward_cpu(const float* x, const float* y_target, const float* W1, const float* b1, const float* W2,
+                          const float* b2, float* dW1, float* db1, float* dW2, float* db2, size_t B, size_t In, size_t H,
+                          size_t Out) {
+    mlp_backward<ExecCpu>(x, y_target, W1, b1, W2, b2, dW1, db1, dW2, db2, B, In, H, Out);
 }
 
 void ref_mlp_grid_infer_cpu(const CGrid* g, int In, int H, int Out, int norm_m1p1, const float* W1, const float* b1,

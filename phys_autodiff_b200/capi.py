@@ -81,7 +81,7 @@ class MLPConfig:
 EXPORTS = [
     "physad_abi_version", "physad_last_error", "physad_error_string",
     "physad_ctx_create", "physad_ctx_destroy", "physad_ctx_sm_count", "physad_set_weights",
-    "physad_mlp_forward_dev", "physad_mlp_forward_host",
+    "physad_mlp_forward_dev", "physad_mlp_forward_host", "physad_mlp_backward_dev", "physad_mlp_backward_host",
     "physad_mlp_grid_infer_dev", "physad_mlp_grid_infer_host",
     "physad_mlp_generate_fields_dev", "physad_mlp_generate_fields_host",
     "physad_phys_residuals_dev", "physad_phys_residuals_host",

@@ -564,6 +564,58 @@ int physad_mlp_forward_host(physad_ctx* c, const float* x, float* y, size_t B) {
     return 0;
 }
 
+int physad_mlp_backward_dev(physad_ctx* c, const float* x, const float* y_target, float* dW1, float* db1, float* dW2,
+                            float* db2, size_t B, void* stream) {
+    if (!c || !x || !y_target || !dW1 || !db1 || !dW2 || !db2) return fail(PHYSAD_E_INVALID, "mlp_backward: null argument");
+    if (!c->has_weights) return fail(PHYSAD_E_NOWEIGHTS, "mlp_backward: no weights set");
+    if (B == 0) return fail(PHYSAD_E_INVALID, "mlp_backward: empty batch (the reference divides by B*Out)");
+    DeviceGuard dg(c->device);
+    cudaStream_t st = cudaStream_t(stream);
+    if (int rc = upload_weights_if_stale(c, st)) return rc;
+    const int In = c->cfg.In, H = c->cfg.H, Out = c->cfg.Out;
+    float *act = nullptr, *gz2 = nullptr, *gz1 = nullptr;
+    CU(cudaMallocAsync(&act, B * size_t(H) * sizeof(float), st));
+    CU(cudaMallocAsync(&gz1, B * size_t(H) * sizeof(float), st));
+    CU(cudaMallocAsync(&gz2, B * size_t(Out) * sizeof(float), st));
+    auto nb = [](size_t n) { return unsigned((n + 255) / 256); };
+    const float scale = 2.f / float(B * size_t(Out));  // src/mlp_cpu.cpp:58
+    k_mlp_generic_hidden<<<nb(B * H), 256, 0, st>>>(x, c->dW1, c->db1, act, B, In, H);
+    k_bwd_gz2<<<nb(B * Out), 256, 0, st>>>(act, c->dW2, c->db2, y_target, gz2, B, H, Out, scale);
+    k_bwd_dW<<<nb(size_t(Out) * H), 256, 0, st>>>(gz2, act, dW2, B, Out, H);
+    k_bwd_db<<<nb(Out), 256, 0, st>>>(gz2, db2, B, Out);
+    k_bwd_gz1<<<nb(B * H), 256, 0, st>>>(gz2, c->dW2, act, gz1, B, H, Out);
+    k_bwd_dW<<<nb(size_t(H) * In), 256, 0, st>>>(gz1, x, dW1, B, H, In);
+    k_bwd_db<<<nb(H), 256, 0, st>>>(gz1, db1, B, H);
+    c->launches += 7;
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(act, st));
+    CU(cudaFreeAsync(gz1, st));
+    CU(cudaFreeAsync(gz2, st));
+    return 0;
+}
+
+int physad_mlp_backward_host(physad_ctx* c, const float* x, const float* y_target, float* dW1, float* db1, float* dW2,
+                             float* db2, size_t B) {
+    if (!c || !x || !y_target || !dW1 || !db1 || !dW2 || !db2) return fail(PHYSAD_E_INVALID, "mlp_backward: null argument");
+    if (!c->has_weights) return fail(PHYSAD_E_NOWEIGHTS, "mlp_backward: no weights set");
+    DeviceGuard dg(c->device);
+    const size_t In = c->cfg.In, H = c->cfg.H, Out = c->cfg.Out;
+    const size_t n[6] = {B * In, B * Out, H * In, H, Out * H, Out};
+    size_t off[7] = {0};
+    for (int k = 0; k < 6; ++k) off[k + 1] = off[k] + ((n[k] * sizeof(float) + 255) & ~size_t(255));
+    if (int rc = ensure_scratch(c, off[6])) return rc;
+    float* d[6];
+    for (int k = 0; k < 6; ++k) d[k] = reinterpret_cast<float*>(c->scratch + off[k]);
+    CU(cudaMemcpyAsync(d[0], x, n[0] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d[1], y_target, n[1] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = physad_mlp_backward_dev(c, d[0], d[1], d[2], d[3], d[4], d[5], B, c->stream)) return rc;
+    float* dst[4] = {dW1, db1, dW2, db2};
+    for (int k = 0; k < 4; ++k)
+        CU(cudaMemcpyAsync(dst[k], d[2 + k], n[2 + k] * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int physad_mlp_grid_infer_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, float t, float* out,
                               void* stream) {
     if (!c || !out) return fail(PHYSAD_E_INVALID, "mlp_grid_infer: null argument");

@@ -60,12 +60,13 @@ void mlp_forward<ExecCuda>(const float* x, const float* W1, const float* b1, con
 }
 
 template <>
-void mlp_backward<ExecCuda>(const float*, const float*, const float*, const float*, const float*, const float*, float*,
-                            float*, float*, float*, std::size_t, std::size_t, std::size_t, std::size_t) {
-    std::fprintf(stderr,
-                 "phys_autodiff_b200: mlp_backward<ExecCuda> (MSE weight gradients) is outside the grid->loss hot path "
-                 "this library implements (SURVEY.md section 8f); use the reference's src/mlp_cuda.cu for it.\n");
-    std::abort();
+void mlp_backward<ExecCuda>(const float* x, const float* y_target, const float* W1, const float* b1, const float* W2,
+                            const float* b2, float* dW1, float* db1, float* dW2, float* db2, std::size_t B,
+                            std::size_t In, std::size_t H, std::size_t Out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    physad_ctx* c = ctx();
+    use_weights(c, In, H, Out, 1, W1, b1, W2, b2);
+    if (int rc = physad_mlp_backward_host(c, x, y_target, dW1, db1, dW2, db2, B)) die("mlp_backward<ExecCuda>", rc);
 }
 
 namespace phys {

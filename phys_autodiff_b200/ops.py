@@ -263,6 +263,17 @@ class Context:
         check(self._lib.physad_mlp_forward_host(self._h, ptr(x), ptr(y), C.c_size_t(B)), "mlp_forward_host")
         return y
 
+    def mlp_backward_host(self, x: np.ndarray, y_target: np.ndarray):
+        """MSE weight gradients (dW1, db1, dW2, db2) -- mlp_backward<ExecCuda>, include/mlp.h:8-9."""
+        x, y_target = _f32(x), _f32(y_target)
+        c = self.cfg
+        B = x.size // c.In
+        dW1 = np.empty(c.H * c.In, np.float32); db1 = np.empty(c.H, np.float32)
+        dW2 = np.empty(c.Out * c.H, np.float32); db2 = np.empty(c.Out, np.float32)
+        check(self._lib.physad_mlp_backward_host(self._h, ptr(x), ptr(y_target), ptr(dW1), ptr(db1), ptr(dW2), ptr(db2),
+                                                 C.c_size_t(B)), "mlp_backward_host")
+        return dW1, db1, dW2, db2
+
     def mlp_grid_infer_host(self, g: Grid, t: float) -> np.ndarray:
         out = np.empty(g.N * 4, np.float32)
         cg = g.c()

@@ -68,6 +68,19 @@ def main():
         c2.update(kind="path", loss_sigma=repr(float(ls)), loss_u=repr(float(lu)))
         meta["cases"].append(c2)
 
+    # 2b. MLP backward (MSE weight gradients) on a small random batch, generic dims
+    rng = np.random.default_rng(7)
+    B, In, H, Out = 23, 5, 12, 3
+    bw = dict(x=rng.uniform(-1, 1, B * In), t=rng.uniform(-1, 1, B * Out), W1=rng.uniform(-.4, .4, H * In),
+              b1=rng.uniform(-.4, .4, H), W2=rng.uniform(-.4, .4, Out * H), b2=rng.uniform(-.4, .4, Out))
+    bw = {k: v.astype(np.float32) for k, v in bw.items()}
+    g4 = R.mlp_backward(bw["x"], bw["t"], bw["W1"], bw["b1"], bw["W2"], bw["b2"], B, In, H, Out)
+    for k, v in bw.items():
+        out["bwd_" + k] = v
+    for k, v in zip(["dW1", "db1", "dW2", "db2"], g4):
+        out["bwd_" + k] = v
+    meta["cases"].append(dict(kind="backward", B=B, In=In, H=H, Out=Out))
+
     # 3. scalar anchors at the BASELINE sizes (SURVEY.md section 7 step 1 lists the same numbers)
     for H in (32, 64, 128):
         g = Grid(64, 64, 64, 1, 1, 1, 2e-3, True)

@@ -97,6 +97,26 @@ def test_mlp_forward_generic_dims_bit_exact(ctx, checker):
         assert bits_equal(got, want), (B, In, H, Out)
 
 
+def test_mlp_backward_bit_exact(ctx, checker, golden):
+    """mlp_backward<ExecCuda>: every gradient entry equals the CPU reference bitwise,
+    incl. the reference's own benchmark shape (test/test_mlp_compare.cpp:17)."""
+    rng = np.random.default_rng(2)
+    for (B, In, H, Out) in [(23, 5, 12, 3), (64, 4, 64, 4), (512, 256, 512, 256), (1, 4, 8, 4)]:
+        x = rng.uniform(-1, 1, B * In).astype(np.float32); t = rng.uniform(-1, 1, B * Out).astype(np.float32)
+        W1 = rng.uniform(-.3, .3, H * In).astype(np.float32); b1 = rng.uniform(-.3, .3, H).astype(np.float32)
+        W2 = rng.uniform(-.3, .3, Out * H).astype(np.float32); b2 = rng.uniform(-.3, .3, Out).astype(np.float32)
+        want = checker.mlp_backward(x, t, W1, b1, W2, b2, B, In, H, Out)
+        ctx.set_weights(_cfg(H, True, In, Out), W1, b1, W2, b2)
+        got = ctx.mlp_backward_host(x, t)
+        for k, a, b in zip(["dW1", "db1", "dW2", "db2"], got, want):
+            assert bits_equal(a, b), (B, In, H, Out, k)
+    arr, meta = golden
+    c = [c for c in meta["cases"] if c["kind"] == "backward"][0]
+    ctx.set_weights(_cfg(c["H"], True, c["In"], c["Out"]), arr["bwd_W1"], arr["bwd_b1"], arr["bwd_W2"], arr["bwd_b2"])
+    for k, a in zip(["dW1", "db1", "dW2", "db2"], ctx.mlp_backward_host(arr["bwd_x"], arr["bwd_t"])):
+        assert bits_equal(a, arr["bwd_" + k]), k
+
+
 @pytest.mark.parametrize("shape,H,per,m1p1", [((48, 48, 32), 64, True, True), ((19, 11, 6), 32, False, False)])
 def test_generate_fields_bit_exact(ctx, checker, shape, H, per, m1p1):
     og = OGrid(*shape, 1, 1, 1, 2e-3, per)

@@ -51,6 +51,15 @@ def test_full_path_matches_golden(port, golden):
         assert float(fl["loss_sigma"]) == float(ls) and float(fl["loss_u"]) == float(lu)
 
 
+def test_mlp_backward_matches_golden(port, golden):
+    arr, meta = golden
+    c = [c for c in meta["cases"] if c["kind"] == "backward"][0]
+    got = port.mlp_backward(arr["bwd_x"], arr["bwd_t"], arr["bwd_W1"], arr["bwd_b1"], arr["bwd_W2"], arr["bwd_b2"],
+                            c["B"], c["In"], c["H"], c["Out"])
+    for k, a in zip(["dW1", "db1", "dW2", "db2"], got):
+        assert bits_equal(a, arr["bwd_" + k]), k
+
+
 def test_anchor_losses_64cubed(port, golden):
     """Scalar anchors at a BASELINE size (also listed in SURVEY.md section 7 / BASELINE.md section 2)."""
     _, meta = golden
@@ -89,6 +98,9 @@ def test_port_equals_reference_library(port, ref):
     W1 = rng.standard_normal(H * In).astype(np.float32); b1 = rng.standard_normal(H).astype(np.float32)
     W2 = rng.standard_normal(Out * H).astype(np.float32); b2 = rng.standard_normal(Out).astype(np.float32)
     assert bits_equal(port.mlp_forward(x, W1, b1, W2, b2, B, In, H, Out), ref.mlp_forward(x, W1, b1, W2, b2, B, In, H, Out))
+    t = rng.standard_normal(B * Out).astype(np.float32)
+    for a, b in zip(port.mlp_backward(x, t, W1, b1, W2, b2, B, In, H, Out), ref.mlp_backward(x, t, W1, b1, W2, b2, B, In, H, Out)):
+        assert bits_equal(a, b)
 
 
 def test_reference_mt_driver_is_bit_identical(ref):

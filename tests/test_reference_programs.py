@@ -43,3 +43,13 @@ def test_reference_benchmark_program_runs(name):
     r = _run(name)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "," in r.stdout  # CSV rows were printed
+
+
+def test_reference_mlp_compare_reports_zero_difference():
+    """test/test_mlp_compare.cpp times mlp_backward CPU vs CUDA (B=512, In=256, H=512, Out=256) and prints the
+    gradient differences without ever failing; with the strict kernels every printed difference must be 0."""
+    import re
+    r = _run("test_mlp_compare")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    diffs = [float(v) for v in re.findall(r"(?:diff|err)[^=:\n]*[=:]\s*([0-9.eE+-]+)", r.stdout)]
+    assert diffs and all(d == 0.0 for d in diffs), r.stdout[-2000:]
