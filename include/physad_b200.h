@@ -192,6 +192,16 @@ int physad_xchg_disconnect(physad_ctx* ctx);
 int physad_fused_loss_allreduce_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float dt,
                                     double* acc_dev, float* R_sigma, float* R_ux, float* R_uy, float* R_uz, void* stream);
 
+/* One rank's whole step with host buffers in ONE call: (optionally) take new weights from the host,
+ * run the fused kernel on `slab` (NULL = whole grid), read the 16-byte result back through pinned memory
+ * and finalise.  exchange != 0 uses the in-kernel peer-memory all-reduce (after physad_xchg_connect), so
+ * the returned losses are the GLOBAL ones on every rank; exchange == 0 returns this slab's share
+ * (w * local sums / N_global).  This is the call bench.py's `e2e` times. */
+int physad_fused_loss_slab_host(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab,
+                                const physad_mlp_config* cfg, const float* W1, const float* b1, const float* W2,
+                                const float* b2, const physad_phys_weights* w, float t, float dt, int exchange,
+                                float* loss_sigma, float* loss_u);
+
 /* L = float(w * acc * (1.0 / N_global)) exactly as src/phys_cpu.cpp:146-148.  Pure host arithmetic. */
 void physad_finalize_loss(const double acc[2], const physad_phys_weights* w, size_t n_global, float* loss_sigma,
                           float* loss_u);

@@ -302,6 +302,8 @@ int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
         case 5: return launch_fused_t<H, 1, 8, 4, 4, true, false>(c, g, s, tc, dt, acc, R, st);   // tile 32x8
         case 6: return launch_fused_t<H, 2, 8, 2, 3, true, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x16, 3 x 256
         case 7: return launch_fused_t<H, 4, 8, 2, 2, true, false>(c, g, s, tc, dt, acc, R, st);   // variant 1 with __syncthreads
+        case 8: return launch_fused_t<H, 1, 16, 4, 2, true, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x16, 512 threads
+        case 9: return launch_fused_t<H, 4, 8, 2, 2, true, true>(c, g, s, tc, dt, acc, R, st, 1); // tile 32x32, ONE 256-thread block/SM
     }
 }
 
@@ -964,6 +966,25 @@ int physad_fused_loss_host(physad_ctx* c, const physad_grid* g, const physad_mlp
         if (host_r[k]) CU(cudaMemcpyAsync(host_r[k], r + k * N, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     physad_finalize_loss(c->h_acc, w, N, loss_sigma, loss_u);
+    return 0;
+}
+
+int physad_fused_loss_slab_host(physad_ctx* c, const physad_grid* g, const physad_slab* slab, const physad_mlp_config* cfg,
+                                const float* W1, const float* b1, const float* W2, const float* b2,
+                                const physad_phys_weights* w, float t, float dt, int exchange, float* loss_sigma,
+                                float* loss_u) {
+    if (!c || !w) return fail(PHYSAD_E_INVALID, "fused_loss_slab: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (cfg) {
+        if (int rc = physad_set_weights(c, cfg, W1, b1, W2, b2)) return rc;
+    }
+    DeviceGuard dg(c->device);
+    const int rc = exchange ? physad_fused_loss_allreduce_dev(c, g, slab, t, dt, c->d_acc, nullptr, nullptr, nullptr, nullptr, c->stream)
+                            : physad_fused_loss_dev(c, g, slab, t, dt, c->d_acc, nullptr, nullptr, nullptr, nullptr, c->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_acc, c->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    physad_finalize_loss(c->h_acc, w, size_t(g->nx) * g->ny * g->nz, loss_sigma, loss_u);
     return 0;
 }
 

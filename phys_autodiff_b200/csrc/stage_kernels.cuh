@@ -224,19 +224,35 @@ __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
         const float* f0[4] = {a.s_0, a.u_0, a.u_0 + N, a.u_0 + 2 * N};
         const float* fm[4] = {a.s_m, a.u_m, a.u_m + N, a.u_m + 2 * N};
         const float* fp[4] = {a.s_p, a.u_p, a.u_p + N, a.u_p + 2 * N};
-        float lo[4], mid[4], hi[4];  // time-t values at z-1, z, z+1 of this column
+        // Software pipeline: the 12 DRAM-bound centre loads of plane z+1 (time-t value that becomes `hi`, and
+        // the t+-dt values) are issued one iteration ahead, so a full plane of arithmetic and L1-hit
+        // neighbour loads covers their latency (ncu on the unpipelined form: long-scoreboard stalls 13 per
+        // issue, DRAM 55 % busy).
+        float lo[4], mid[4], hi[4];      // time-t values at z-1, z, z+1 of this column
+        float tp[4], tm[4];              // t+dt / t-dt values at z
         {
             const size_t pm = size_t(nb1(z0 - 1, a.nz, per)) * pln + oc, pc = size_t(z0) * pln + oc;
+            const size_t pn = size_t(nb1(z0 + 1, a.nz, per)) * pln + oc;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { lo[c] = __ldg(f0[c] + pm); mid[c] = __ldg(f0[c] + pc); }
+            for (int c = 0; c < 4; ++c) {
+                lo[c] = __ldg(f0[c] + pm); mid[c] = __ldg(f0[c] + pc); hi[c] = __ldg(f0[c] + pn);
+                tp[c] = __ldg(fp[c] + pc); tm[c] = __ldg(fm[c] + pc);
+            }
         }
         for (int z = z0; z < z1; ++z) {
-            const size_t pz = size_t(z) * pln, pzp = size_t(nb1(z + 1, a.nz, per)) * pln;
+            const size_t pz = size_t(z) * pln;
+            // prefetch for the next iteration (plane z+1's t+-dt values, plane z+2's time-t value)
+            const int zn = min(z + 1, a.nz - 1);  // clamped only to stay in bounds on the last iteration
+            const size_t pzn = size_t(zn) * pln + oc, pzn2 = size_t(nb1(zn + 1, a.nz, per)) * pln + oc;
+            float ntp[4], ntm[4], nhi[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                ntp[c] = __ldg(fp[c] + pzn); ntm[c] = __ldg(fm[c] + pzn); nhi[c] = __ldg(f0[c] + pzn2);
+            }
             float dT[4], gx[4], gy[4], gz[4], R[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                hi[c] = __ldg(f0[c] + pzp + oc);
-                dT[c] = central_diff(__ldg(fp[c] + pz + oc), __ldg(fm[c] + pz + oc), a.inv2dt);
+                dT[c] = central_diff(tp[c], tm[c], a.inv2dt);
                 gx[c] = central_diff(__ldg(f0[c] + pz + oxp), __ldg(f0[c] + pz + oxm), a.inv2hx);
                 gy[c] = central_diff(__ldg(f0[c] + pz + oyp), __ldg(f0[c] + pz + oym), a.inv2hy);
                 gz[c] = central_diff(hi[c], lo[c], a.inv2hz);
@@ -254,7 +270,7 @@ __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
                 acc_u += double(R[1]) * double(R[1]) + double(R[2]) * double(R[2]) + double(R[3]) * double(R[3]);
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { lo[c] = mid[c]; mid[c] = hi[c]; }
+            for (int c = 0; c < 4; ++c) { lo[c] = mid[c]; mid[c] = hi[c]; hi[c] = nhi[c]; tp[c] = ntp[c]; tm[c] = ntm[c]; }
         }
     }
     if (REDUCE) {

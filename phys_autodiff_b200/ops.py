@@ -256,6 +256,26 @@ class Context:
         self.cfg = cfg
         return (np.float32(ls.value), np.float32(lu.value)) + ((tuple(R),) if want_residuals else ())
 
+    def prepare_step_host(self, g: Grid, cfg: MLPConfig, W1, b1, W2, b2, pw: PhysWeights, t: float, dt: float, slab=None):
+        """One rank's whole step through the host-buffer C-ABI call (weights in, two losses out), pre-marshalled.
+        With connect_peers() done the losses are global (in-kernel exchange); otherwise they are this slab's."""
+        W1, b1, W2, b2 = _f32(W1), _f32(b1), _f32(W2), _f32(b2)
+        cs, _ = self._slab(g, slab)
+        cg, cc, cw = g.c(), cfg.c(), pw.c()
+        ls, lu = C.c_float(), C.c_float()
+        fn, h = self._lib.physad_fused_loss_slab_host, self._h
+        args = (C.byref(cg), C.byref(cs), C.byref(cc), ptr(W1), ptr(b1), ptr(W2), ptr(b2), C.byref(cw), C.c_float(t),
+                C.c_float(dt), C.c_int(1 if self._peers else 0), C.byref(ls), C.byref(lu))
+        keep = (cg, cs, cc, cw, W1, b1, W2, b2)
+        self.cfg = cfg
+
+        def step(_keep=keep):
+            rc = fn(h, *args)
+            if rc:
+                check(rc, "fused_loss_slab_host")
+            return ls.value, lu.value
+        return step
+
     def mlp_forward_host(self, x: np.ndarray) -> np.ndarray:
         x = _f32(x)
         B = x.size // self.cfg.In

@@ -25,6 +25,9 @@ ctx.set_weights(MLPConfig(4, 64, 4, True), *w)
 ls, lu, R = ctx.fused_loss(g, PhysWeights(1.3, 0.7), 0.25, 2e-3, want_residuals=True)      # NCCL all-reduce
 assert ctx.connect_peers()
 p2p = [ctx.fused_loss(g, PhysWeights(1.3, 0.7), 0.25, 2e-3) for _ in range(5)]             # in-kernel exchange, 5 epochs
+host_step = ctx.prepare_step_host(g, MLPConfig(4, 64, 4, True), *w, PhysWeights(1.3, 0.7), 0.25, 2e-3,
+                                  slab=ops.slab_for_rank(g.nz, rank, world))
+p2p += [host_step() for _ in range(3)]                                                     # one-call host form
 ctx.disconnect_peers()
 z0, z1 = ops.slab_for_rank(g.nz, rank, world)
 # single-GPU answer for the same grid on this rank's device (no process group involved)
