@@ -51,6 +51,23 @@ def ncu_dram_traffic():
         return None
 
 
+def ncu_fma_pipe_active():
+    """sm__pipe_fma_cycles_active (% of active cycles) of the fused kernel from the same committed capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_fused_default_summary.json")) as fh:
+            return float(json.load(fh)[0]["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"][0])
+    except Exception:
+        return None
+
+
+def executed_flops_per_point(H: int) -> float:
+    """fp32 lane-operations the default kernel actually executes per point: the three
+    time slices share the layer-1 prefix and 4 columns share b1 + W1[h,0]x, so layer 1 costs 6.75 instead of 24
+    ops per hidden unit; layer 2 keeps its 24; + ring (192 of 2048 columns re-evaluated at time t, 15 ops per
+    hidden unit), + z-halo planes (~2 per 55), + ~55 for stencil and reduction."""
+    return 30.75 * H + (192.0 / 2048.0) * 15.0 * H + (2.0 / 55.0) * 12.75 * H + 55.0
+
+
 def strict_fp32_peak():
     """Measured FMUL+FADD (non-contracted) pipe peak of this pool's B200, TFLOP/s, and where it came from."""
     p = os.path.join(ROOT, "profiles", "r01_microbench_fp32_long.json")
@@ -409,8 +426,14 @@ def main():
                          "frac": achieved / peak_strict, "traffic": ncu_dram_traffic() if (H == 64 and n == 256 and world == 1) else None,
                          "peak_source": peak_src, "peak_ffma": peak_ffma,
                          "flops_per_point": flops_per_point(H), "kernel_ms_mean": k_mean, "kernel_ms_min": k_min,
-                         "note": "algorithmic flops (51H+68)/point x slab points / CUDA-event kernel time; peak = measured "
-                                 "non-contracted FMUL+FADD rate (parity mode cannot use FFMA); HBM traffic is ~0 by design"},
+                         "executed_flops_per_point": executed_flops_per_point(H),
+                         "frac_executed": executed_flops_per_point(H) * slab_pts / (k_mean * 1e-3) / 1e12 / peak_strict,
+                         "fma_pipe_active_pct_ncu": ncu_fma_pipe_active() if (H == 64 and n == 256 and world == 1) else None,
+                         "note": "achieved = ALGORITHMIC flops (51H+68)/point x slab points / CUDA-event kernel time; peak = measured "
+                                 "non-contracted FMUL+FADD rate (parity mode cannot use FFMA). frac > 1 because the kernel "
+                                 "executes fewer operations than the algorithmic count (shared layer-1 prefix across the three "
+                                 "time slices; bit-identical results): frac_executed counts what it really executes and agrees "
+                                 "with ncu's FMA-pipe utilisation. HBM traffic is ~0 by design"},
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall,
             "step_ms": {"min": min(per), "median": statistics.median(per), "max": max(per)},
