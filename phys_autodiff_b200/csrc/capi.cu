@@ -50,6 +50,12 @@ struct physad_ctx {
     size_t scratch_cap = 0;
     uint64_t launches = 0;
     int fused_variant = 0;
+    // axis-coordinate tables cxs[nx] | cys[ny] | czs[nz] on the device, cached per (grid, norm)
+    struct CoordTables {
+        int key[5] = {0, 0, 0, 0, 0};  // nx, ny, nz, norm, valid
+        float* dev = nullptr;
+        size_t cap = 0;
+    } tab;
     // launch plan of the fused kernel: coordinate tables + per-block work ranges, cached per geometry
     struct FusedPlan {
         int key[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // nx, ny, nz, z_begin, z_end, norm, TX, TY, slots, valid
@@ -154,6 +160,30 @@ float host_axis_coord(int i, int n, bool m1p1) {
     return m1p1 ? two_u - 1.f : float(u);
 }
 
+// Device tables of the axis coordinates of every x, y and z index (a few KB), so kernels neither divide
+// nor recompute them per point.  Rebuilt only when the grid extents or the normalisation change.
+int ensure_coord_tables(physad_ctx* c, const physad_grid* g, cudaStream_t st) {
+    const int key[5] = {g->nx, g->ny, g->nz, c->cfg.norm, 1};
+    auto& t = c->tab;
+    if (std::memcmp(key, t.key, sizeof(key)) == 0) return 0;
+    const bool m1p1 = c->cfg.norm == 1;
+    const size_t nf = size_t(g->nx) + g->ny + g->nz;
+    std::vector<float> host(nf);
+    for (int i = 0; i < g->nx; ++i) host[i] = host_axis_coord(i, g->nx, m1p1);
+    for (int i = 0; i < g->ny; ++i) host[g->nx + i] = host_axis_coord(i, g->ny, m1p1);
+    for (int i = 0; i < g->nz; ++i) host[g->nx + g->ny + i] = host_axis_coord(i, g->nz, m1p1);
+    if (nf > t.cap) {
+        if (t.dev) CU(cudaFree(t.dev));
+        t.dev = nullptr; t.cap = 0;
+        CU(cudaMalloc(&t.dev, nf * sizeof(float)));
+        t.cap = nf;
+    }
+    CU(cudaStreamSynchronize(st));  // rare path; keeps the pageable staging vector's lifetime trivial
+    CU(cudaMemcpy(t.dev, host.data(), nf * sizeof(float), cudaMemcpyHostToDevice));
+    std::memcpy(t.key, key, sizeof(key));
+    return 0;
+}
+
 // Split the tile-plane sequence (tiles x nzl planes, tile-major) into at most `slots` contiguous ranges
 // of equal COST, where a range pays `seg_cost` extra for every z-segment it starts (its two time-t-only
 // halo planes + prologue).  Greedy fill under a cost cap, cap found by bisection.
@@ -197,42 +227,30 @@ std::vector<int> balanced_ranges(int tiles, int nzl, long long slots, double seg
 
 int build_fused_plan(physad_ctx* c, const physad_grid* g, const physad_slab& s, int TX, int TY, long long slots,
                      cudaStream_t st) {
-    const int key[10] = {g->nx, g->ny, g->nz, s.z_begin, s.z_end, c->cfg.norm, TX, TY, int(slots), 1};
+    if (int rc = ensure_coord_tables(c, g, st)) return rc;
     auto& p = c->plan;
-    if (std::memcmp(key, p.key, sizeof(key)) == 0) return 0;
-    const bool m1p1 = c->cfg.norm == 1;
-    const int tiles = ((g->nx + TX - 1) / TX) * ((g->ny + TY - 1) / TY), nzl = s.z_end - s.z_begin;
-    long long want = std::min<long long>(slots, (long long)tiles * nzl);
-    std::vector<int> ranges = balanced_ranges(tiles, nzl, want, 0.9);
-    const size_t nf = size_t(g->nx) + g->ny + g->nz;
-    std::vector<char> host(nf * sizeof(float) + ranges.size() * sizeof(int));
-    float* f = reinterpret_cast<float*>(host.data());
-    for (int i = 0; i < g->nx; ++i) f[i] = host_axis_coord(i, g->nx, m1p1);
-    for (int i = 0; i < g->ny; ++i) f[g->nx + i] = host_axis_coord(i, g->ny, m1p1);
-    for (int i = 0; i < g->nz; ++i) f[g->nx + g->ny + i] = host_axis_coord(i, g->nz, m1p1);
-    std::memcpy(host.data() + nf * sizeof(float), ranges.data(), ranges.size() * sizeof(int));
-    if (host.size() > p.cap) {
-        if (p.dev) CU(cudaFree(p.dev));
-        p.dev = nullptr; p.cap = 0;
-        CU(cudaMalloc(&p.dev, host.size()));
-        p.cap = host.size();
-    }
-    // rare (geometry change): a synchronous copy keeps the pageable staging vector's lifetime trivial
-    CU(cudaStreamSynchronize(st));
-    CU(cudaMemcpy(p.dev, host.data(), host.size(), cudaMemcpyHostToDevice));
-    p.cxs = reinterpret_cast<const float*>(p.dev);
+    p.cxs = c->tab.dev;
     p.cys = p.cxs + g->nx;
     p.czs = p.cys + g->ny;
-    p.ranges = reinterpret_cast<const int*>(p.dev + nf * sizeof(float));
+    const int key[10] = {g->nx, g->ny, g->nz, s.z_begin, s.z_end, c->cfg.norm, TX, TY, int(slots), 1};
+    if (std::memcmp(key, p.key, sizeof(key)) == 0) return 0;
+    const int tiles = ((g->nx + TX - 1) / TX) * ((g->ny + TY - 1) / TY), nzl = s.z_end - s.z_begin;
+    const long long want = std::min<long long>(slots, (long long)tiles * nzl);
+    const std::vector<int> ranges = balanced_ranges(tiles, nzl, want, 0.9);
+    const size_t bytes = ranges.size() * sizeof(int);
+    if (bytes > p.cap) {
+        if (p.dev) CU(cudaFree(p.dev));
+        p.dev = nullptr; p.cap = 0;
+        CU(cudaMalloc(&p.dev, bytes));
+        p.cap = bytes;
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(p.dev, ranges.data(), bytes, cudaMemcpyHostToDevice));
+    p.ranges = reinterpret_cast<const int*>(p.dev);
     p.blocks = int(ranges.size()) - 1;
     std::memcpy(p.key, key, sizeof(key));
     return 0;
 }
-
-struct FusedGeom {
-    int tiles_x, tiles_y, nchunks;
-    size_t smem;
-};
 
 template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR = false>
 int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool xchg, double* acc,
@@ -338,13 +356,17 @@ int launch_fused(physad_ctx* c, const physad_grid* g, const physad_slab& s, floa
 
 // ---- MLP over the grid ---------------------------------------------------------------------
 template <int H, bool FIELDS>
-int launch_grid_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], const GridInferArgs& a,
+int launch_grid_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], GridInferArgs a,
                   cudaStream_t st) {
-    const size_t n = size_t(s.z_end - s.z_begin) * g->ny * g->nx;
-    if (n == 0) return 0;
+    const int nzl = s.z_end - s.z_begin;
+    if (nzl == 0) return 0;
+    if (nzl > 65535) return fail(PHYSAD_E_UNSUPPORTED, "grid MLP kernels: more than 65535 planes per call");
+    if (int rc = ensure_coord_tables(c, g, st)) return rc;
+    a.cxs = c->tab.dev; a.cys = a.cxs + g->nx; a.czs = a.cys + g->ny;
     MlpConst<H> k;
     fill_const<H>(c, tc, k);
-    k_mlp_grid<H, FIELDS, 4><<<unsigned((n + 255) / 256), 256, 0, st>>>(k, a);
+    const dim3 grid(unsigned((g->nx + 31) / 32), unsigned((g->ny + 31) / 32), unsigned(nzl));
+    k_mlp_grid<H, FIELDS, 2><<<grid, 256, 0, st>>>(k, a);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -466,6 +488,7 @@ int physad_ctx_destroy(physad_ctx* c) {
     physad_xchg_disconnect(c);
     cudaFree(c->xbuf);
     cudaFree(c->plan.dev);
+    cudaFree(c->tab.dev);
     cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_acc); cudaFree(c->scratch);
     cudaFreeHost(c->h_acc);
     cudaStreamDestroy(c->stream);

@@ -21,38 +21,53 @@ struct GridInferArgs {
     int nx, ny, nz;
     int z_begin, z_end;
     int m1p1;
+    const float* cxs; const float* cys; const float* czs;  // axis-coordinate tables (capi.cu: ensure_coord_tables)
     float4* out_aos;    // FIELDS=false
     float* sigma[3];    // FIELDS=true: t-dt, t, t+dt
     float* u[3];
 };
 
+// Block = 32 x 8 threads on a 32 x 32 (x,y) patch of one z plane; a thread evaluates 4 points that share x
+// (rows ty, ty+8, ...), which shares b1 + W1[h,0]x and W1[h,2]z between them exactly as in the fused kernel;
+// coordinates come from the index tables (no per-point integer or IEEE division); stores are coalesced rows.
 template <int H, bool FIELDS, int UNROLL>
 __global__ void __launch_bounds__(256) k_mlp_grid(const __grid_constant__ MlpConst<H> w, const GridInferArgs a) {
+    constexpr int P = 4;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y0 = blockIdx.y * 32 + (threadIdx.x >> 5);
+    const int z = a.z_begin + blockIdx.z;
     const size_t n = size_t(a.z_end - a.z_begin) * a.ny * a.nx;
-    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int x = int(i % a.nx);
-    const size_t r = i / a.nx;
-    const int y = int(r % a.ny);
-    const int z = a.z_begin + int(r / a.ny);
-    const bool m1p1 = a.m1p1 != 0;
-    const float cx = axis_coord(x, a.nx, m1p1);
-    const float cy[1] = {axis_coord(y, a.ny, m1p1)};
-    const float cz = axis_coord(z, a.nz, m1p1);
-    if (FIELDS) {
-        float o[1][3][4];
-        mlp_eval<H, 3, 1, UNROLL, true>(w, cx, cy, cz, o);
+    const float cx = __ldg(a.cxs + min(x, a.nx - 1));
+    const float cz = __ldg(a.czs + z);
+    float cy[P];
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            a.sigma[s][i] = o[0][s][0];
-            a.u[s][i] = o[0][s][1];
-            a.u[s][n + i] = o[0][s][2];
-            a.u[s][2 * n + i] = o[0][s][3];
+    for (int j = 0; j < P; ++j) cy[j] = __ldg(a.cys + min(y0 + 8 * j, a.ny - 1));
+    if (FIELDS) {
+        float o[P][3][4];
+        mlp_eval<H, 3, P, UNROLL, true>(w, cx, cy, cz, o);
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int y = y0 + 8 * j;
+            if (x < a.nx && y < a.ny) {
+                const size_t i = (size_t(blockIdx.z) * a.ny + y) * a.nx + x;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    a.sigma[s][i] = o[j][s][0];
+                    a.u[s][i] = o[j][s][1];
+                    a.u[s][n + i] = o[j][s][2];
+                    a.u[s][2 * n + i] = o[j][s][3];
+                }
+            }
         }
     } else {
-        float o[1][1][4];
-        mlp_eval<H, 1, 1, UNROLL, true>(w, cx, cy, cz, o);
-        a.out_aos[i] = make_float4(o[0][0][0], o[0][0][1], o[0][0][2], o[0][0][3]);
+        float o[P][1][4];
+        mlp_eval<H, 1, P, UNROLL, true>(w, cx, cy, cz, o);
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int y = y0 + 8 * j;
+            if (x < a.nx && y < a.ny)
+                a.out_aos[(size_t(blockIdx.z) * a.ny + y) * a.nx + x] = make_float4(o[j][0][0], o[j][0][1], o[j][0][2], o[j][0][3]);
+        }
     }
 }
 
