@@ -225,7 +225,7 @@ def main():
     ap.add_argument("--emulate-planes", type=int, default=0, help="with --emulate-rank-of: slab = first P planes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="skip the NVML clock sampler thread (diagnostics)")
-    ap.add_argument("--extra", action="store_true", help="also time H=32 and H=128 (reported under 'extra')")
+    ap.add_argument("--no-extra", action="store_true", help="skip the H=32 / H=128 width sweep reported under 'extra' (N=1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -385,13 +385,13 @@ def main():
     h2d = sum(int(a.nbytes) for a in w)
 
     extra = {}
-    if args.extra and world == 1:
+    if not args.no_extra and world == 1 and args.hidden == 64:
         for H2 in (32, 128):
             w2 = ops.mlp_random_init(H2, SEED, SCALE)
             ctx.set_weights(MLPConfig(4, H2, 4, True), *w2)
             t_ms, _, _, _, _ = timed(10, 3)
-            extra[f"H{H2}"] = {"value": g.N * 10 / (t_ms * 1e-3), "unit": UNIT,
-                               "tflops_algorithmic": flops_per_point(H2) * g.N * 10 / (t_ms * 1e-3) / 1e12}
+            extra[f"H{H2}"] = {"value": g.N * 10 / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / 10,
+                               "roofline_frac": flops_per_point(H2) * g.N * 10 / (t_ms * 1e-3) / 1e12 / peak_strict}
         ctx.set_weights(cfg, *w)
 
     cpu = None
