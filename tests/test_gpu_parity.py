@@ -169,9 +169,9 @@ def test_fused_and_nonfused_names_agree(ctx):
 
 @pytest.mark.parametrize("shape,per", [((33, 18, 7), True), ((33, 18, 7), False), ((5, 1, 1), False), ((1, 1, 1), True),
                                        ((2, 2, 2), True), ((64, 64, 64), False),
-                                       # nx % 4 == 0: the bulk-copy staged kernel (stencil_bulk.cuh); ragged row tiles,
-                                       # fewer rows than a tile, single planes, the 2-row variant (nx > 345), and a
-                                       # row too long for shared memory (falls back to the register kernel)
+                                       # more shapes with nx % 4 == 0 (vectorisable rows): ragged row tiles,
+                                       # fewer rows than a tile, single planes, long rows,
+                                       # and a mid-sized anisotropic grid
                                        ((36, 18, 7), True), ((36, 18, 7), False), ((8, 3, 5), True), ((8, 3, 1), False),
                                        ((4, 1, 2), True), ((352, 5, 3), True), ((520, 6, 2), False), ((600, 4, 2), True),
                                        ((128, 96, 40), True)])
