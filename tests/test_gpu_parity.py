@@ -309,6 +309,30 @@ def test_fused_is_deterministic(ctx, checker):
         assert np.array_equal(ctx.fused_loss_acc(_g(og), 0.25, 2e-3).cpu().numpy(), a)
 
 
+@pytest.mark.parametrize("shape,H,per", [((96, 80, 37), 64, True), ((70, 37, 19), 128, False), ((130, 66, 11), 32, True)])
+def test_fused_repeatability_stress(ctx, checker, shape, H, per):
+    """The split-phase barrier lets warps run up to one plane apart over a 4-deep ring of plane buffers; a
+    missed hazard would show up as run-to-run differences.  40 launches must give bit-identical residuals
+    (and they must equal the scalar, __syncthreads-based variant 3)."""
+    import torch
+    og = OGrid(*shape, 1, 1, 1, 2e-3, per)
+    g = _g(og)
+    w = checker.mlp_random_init(H, 777, 0.25)
+    ctx.set_weights(_cfg(H), *w)
+    ctx.set_fused_variant(3)
+    ref = [torch.empty(og.N, device="cuda") for _ in range(4)]
+    acc_ref = ctx.fused_loss_acc(g, 0.25, 2e-3, residuals=ref).clone()
+    ctx.set_fused_variant(0)
+    try:
+        for it in range(40):
+            R = [torch.full((og.N,), float("nan"), device="cuda") for _ in range(4)]
+            acc = ctx.fused_loss_acc(g, 0.25, 2e-3, residuals=R)
+            assert all(torch.equal(a, b) for a, b in zip(R, ref)), it
+            assert torch.allclose(acc, acc_ref, rtol=1e-12, atol=0), it
+    finally:
+        ctx.set_fused_variant(0)
+
+
 def test_slab_partials_sum_to_whole(ctx, checker):
     """Multi-GPU arithmetic on one GPU: slabs for world sizes 2/3/8 (halo planes recomputed, incl. the
     periodic wrap for the first/last slab) reproduce the whole-grid residuals and sums."""
