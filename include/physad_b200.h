@@ -20,6 +20,9 @@
  *   AoS [sigma,ux,uy,uz] per point (include/mlp_grid.h:16).
  *   There is no CPU fallback anywhere behind this header: without a CUDA device every compute
  *   entry point returns an error.
+ *   Threading: a context is NOT thread-safe -- serialise calls on it (use one context per host thread or
+ *   per stream).  The reducing calls (fused_loss*, phys_loss*) share per-context reduction scratch, so two of
+ *   them on the same context must be ordered on the device (same stream, or an event between streams).
  */
 #ifndef PHYSAD_B200_H
 #define PHYSAD_B200_H

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace physad;
@@ -50,6 +51,9 @@ struct physad_ctx {
     size_t scratch_cap = 0;
     uint64_t launches = 0;
     int fused_variant = 0;
+    // per-kernel launch facts on THIS device (opt-in shared memory set, resident blocks per SM): function
+    // attributes are per device, so they are cached per context, not per process
+    std::unordered_map<const void*, int> blocks_per_sm;
     // axis-coordinate tables cxs[nx] | cys[ny] | czs[nz] on the device, cached per (grid, norm)
     struct CoordTables {
         int key[5] = {0, 0, 0, 0, 0};  // nx, ny, nz, norm, valid
@@ -258,16 +262,14 @@ int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
     constexpr int TX = 32, TY = TYB * P;
     auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB, PACKED, SPLITBAR>;
     const size_t smem = size_t(4) * 4 * (TX + 2) * (TY + 2) * sizeof(float);
-    // per-kernel launch facts, queried once per process (this sits on the per-step host path)
-    static int per_sm = 0;
-    static long long env_blocks = -1;
+    // per-kernel launch facts, queried once per context (this sits on the per-step host path)
+    static const long long env_blocks = getenv("PHYSAD_FUSED_BLOCKS") ? atoll(getenv("PHYSAD_FUSED_BLOCKS")) : 0;  // tuning aid
+    int& per_sm = c->blocks_per_sm[reinterpret_cast<const void*>(kern)];
     if (per_sm == 0) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int q = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, 32 * TYB, smem));
         if (q < 1) return fail(PHYSAD_E_UNSUPPORTED, "fused kernel does not fit on an SM");
-        const char* e = getenv("PHYSAD_FUSED_BLOCKS");
-        env_blocks = e ? atoll(e) : 0;
         per_sm = q;
     }
     const int tiles_x = (g->nx + TX - 1) / TX, tiles_y = (g->ny + TY - 1) / TY;
@@ -471,11 +473,19 @@ int physad_ctx_create(physad_ctx** out, int device) {
     physad_ctx* c = new physad_ctx();
     c->device = device;
     c->sm_count = p.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&c->ticket, sizeof(unsigned int)));
-    CU(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
-    CU(cudaMalloc(&c->d_acc, 2 * sizeof(double)));
-    CU(cudaMallocHost(&c->h_acc, 2 * sizeof(double)));
+    auto init = [c]() -> int {
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&c->ticket, sizeof(unsigned int)));
+        CU(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
+        CU(cudaMalloc(&c->d_acc, 2 * sizeof(double)));
+        CU(cudaMallocHost(&c->h_acc, 2 * sizeof(double)));
+        return 0;
+    };
+    if (int rc = init()) {
+        const std::string msg = g_err;  // destroy() must not clobber the reason
+        physad_ctx_destroy(c);
+        return fail(rc, msg);
+    }
     *out = c;
     return 0;
 }
@@ -483,15 +493,15 @@ int physad_ctx_create(physad_ctx** out, int device) {
 int physad_ctx_destroy(physad_ctx* c) {
     if (!c) return 0;
     DeviceGuard dg(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->dW1); cudaFree(c->db1); cudaFree(c->dW2); cudaFree(c->db2);
     physad_xchg_disconnect(c);
     cudaFree(c->xbuf);
     cudaFree(c->plan.dev);
     cudaFree(c->tab.dev);
     cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_acc); cudaFree(c->scratch);
-    cudaFreeHost(c->h_acc);
-    cudaStreamDestroy(c->stream);
+    if (c->h_acc) cudaFreeHost(c->h_acc);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }
