@@ -223,6 +223,9 @@ def main():
     ap.add_argument("--emulate-rank-of", type=int, default=0,
                     help="tuning aid: time only the kernel for rank 0's slab of an N-rank run on ONE GPU and exit")
     ap.add_argument("--emulate-planes", type=int, default=0, help="with --emulate-rank-of: slab = first P planes")
+    ap.add_argument("--exact-residuals", action="store_true",
+                    help="stencil/residual arithmetic in double exactly as the CPU reference (bit-identical residuals) "
+                         "instead of the default fp32-with-FMA mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="skip the NVML clock sampler thread (diagnostics)")
     ap.add_argument("--no-extra", action="store_true", help="skip the H=32 / H=128 width sweep reported under 'extra' (N=1 only)")
@@ -256,6 +259,8 @@ def main():
     ctx = ops.Context(local)
     if args.variant >= 0:
         ctx.set_fused_variant(args.variant)
+    if args.exact_residuals:
+        ctx.set_exact_residuals(True)
     ctx.set_weights(cfg, *w)
     slab = slab_for_rank(n, rank, world)
     acc = torch.zeros(2, dtype=torch.float64, device="cuda")
@@ -413,7 +418,9 @@ def main():
                                    f"h 1, periodic, MinusOneToOne (test_mlp_phys_perf.cpp:21-23 at 256^3)",
                        "hidden": H, "grid": [n, n, n], "parallelism": f"z-slab x{world}, halo recomputed, 1 all-reduce of 2 doubles "
                                       + ("inside the kernel over NVLink peer memory" if p2p else "(NCCL)" if world > 1 else "(n/a)"),
-                       "mode": "strict fp32 (FMUL+FADD, bit-exact MLP)",
+                       "mode": "strict fp32 MLP (FMUL+FADD, bit-exact); residual arithmetic "
+                               + ("in double exactly as the CPU reference (bit-identical residuals)" if args.exact_residuals
+                                  else "fp32 with FMAs (as the reference's CUDA kernels; ~1e-7 of the CPU)"),
                        "l2": "no HBM-resident inputs (coordinates from index, weights in the constant bank); L2 flushed "
                              "between timed steps with a 256 MiB write outside the per-step events",
                        "fused_variant": args.variant},

@@ -222,6 +222,14 @@ void physad_mlp_random_init(int In, int H, int Out, unsigned int seed, float sca
  * negative status.  Exposed so the partition can be tested without a GPU. */
 int physad_plan_ranges(int tiles, int planes, int slots, int* out, int out_cap);
 
+/* Residual arithmetic mode.  0 (default): the stencil and the residual sums in fp32 with fused multiply-adds,
+ * like the reference's own CUDA kernels (measured within ~1e-7 * max|R| of the CPU reference; gate 1e-5).
+ * 1: evaluated in double exactly as cpu_phys_residuals does (src/phys_cpu.cpp:66-109), so residuals are
+ * BIT-IDENTICAL to the CPU reference (given the bit-exact MLP); costs ~5 % on the fused kernel and makes the
+ * HBM-bound stage-wise kernels FP64/conversion-bound (0.24 -> 0.30 ms at 256^3).  Applies to the fused kernel
+ * and to the stage-wise physics kernels.  Returns the previous value. */
+int physad_set_exact_residuals(physad_ctx* ctx, int on);
+
 /* Tuning knob for experiments: selects the fused-kernel variant (0 = default). Returns the previous value. */
 int physad_set_fused_variant(physad_ctx* ctx, int variant);
 /* Number of kernel launches this context has enqueued since creation (bench.py's gpu_launches). */

@@ -51,6 +51,7 @@ struct physad_ctx {
     size_t scratch_cap = 0;
     uint64_t launches = 0;
     int fused_variant = 0;
+    int exact_residuals = 0;  // 1: residual arithmetic in double exactly as the CPU reference; 0: fp32 with FMAs
     // per-kernel launch facts on THIS device (opt-in shared memory set, resident blocks per SM): function
     // attributes are per device, so they are cached per context, not per process
     std::unordered_map<const void*, int> blocks_per_sm;
@@ -116,6 +117,7 @@ int check_slab(const physad_grid* g, const physad_slab* s, physad_slab* out) {
 
 // float(1 / (2 h)) with the quotient formed in double as the CPU reference does (src/phys_cpu.cpp:38-41)
 float inv2(float h) { return float(1.0 / (2.0 * double(h))); }
+double inv2d(float h) { return 1.0 / (2.0 * double(h)); }  // exactly src/phys_cpu.cpp:38-41
 
 int template_h(int H) { return H <= 32 ? 32 : (H <= 64 ? 64 : (H <= 128 ? 128 : 0)); }
 
@@ -256,11 +258,11 @@ int build_fused_plan(physad_ctx* c, const physad_grid* g, const physad_slab& s, 
     return 0;
 }
 
-template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR = false>
-int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool xchg, double* acc,
+template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR, bool DPRES>
+int launch_fused_d(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool xchg, double* acc,
                    float* const R[4], cudaStream_t st, int blocks_per_sm_cap = 0) {
     constexpr int TX = 32, TY = TYB * P;
-    auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB, PACKED, SPLITBAR>;
+    auto kern = k_fused_mlp_phys_loss<H, P, TYB, UNROLL, MINB, PACKED, SPLITBAR, DPRES>;
     const size_t smem = size_t(4) * 4 * (TX + 2) * (TY + 2) * sizeof(float);
     // per-kernel launch facts, queried once per context (this sits on the per-step host path)
     static const long long env_blocks = getenv("PHYSAD_FUSED_BLOCKS") ? atoll(getenv("PHYSAD_FUSED_BLOCKS")) : 0;  // tuning aid
@@ -285,6 +287,7 @@ int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
     a.cxs = c->plan.cxs; a.cys = c->plan.cys; a.czs = c->plan.czs; a.ranges = c->plan.ranges;
     a.m1p1 = c->cfg.norm == 1; a.periodic = g->periodic != 0;
     a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
+    a.inv2dt_d = inv2d(g->dt); a.inv2hx_d = inv2d(g->hx); a.inv2hy_d = inv2d(g->hy); a.inv2hz_d = inv2d(g->hz);
     if (int rc = ensure_partials(c, size_t(blocks))) return rc;
     a.partials = c->partials; a.ticket = c->ticket; a.acc_out = acc;
     for (int k = 0; k < 4; ++k) a.R[k] = R[k];
@@ -298,6 +301,14 @@ int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
     c->launches++;
     CU(cudaGetLastError());
     return 0;
+}
+
+template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR = false>
+int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool xchg, double* acc,
+                   float* const R[4], cudaStream_t st, int blocks_per_sm_cap = 0) {
+    if (c->exact_residuals)
+        return launch_fused_d<H, P, TYB, UNROLL, MINB, PACKED, SPLITBAR, true>(c, g, s, tc, xchg, acc, R, st, blocks_per_sm_cap);
+    return launch_fused_d<H, P, TYB, UNROLL, MINB, PACKED, SPLITBAR, false>(c, g, s, tc, xchg, acc, R, st, blocks_per_sm_cap);
 }
 
 template <int H>
@@ -393,6 +404,7 @@ template <bool WRITE_R, bool REDUCE, bool SCALE>
 int launch_phys(physad_ctx* c, const physad_grid* g, PhysArgs a, cudaStream_t st) {
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.periodic = g->periodic != 0;
     a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
+    a.inv2dt_d = inv2d(g->dt); a.inv2hx_d = inv2d(g->hx); a.inv2hy_d = inv2d(g->hy); a.inv2hz_d = inv2d(g->hz);
     // 32 x 8 column tiles, each marching a z chunk; enough chunks for ~16 blocks per SM
     const unsigned tx = unsigned((g->nx + 31) / 32), ty = unsigned((g->ny + 7) / 8);
     if (ty > 65535u) return fail(PHYSAD_E_UNSUPPORTED, "phys kernels: ny > 524280");
@@ -406,7 +418,8 @@ int launch_phys(physad_ctx* c, const physad_grid* g, PhysArgs a, cudaStream_t st
         if (int rc = ensure_partials(c, size_t(tx) * ty * nch)) return rc;
         a.partials = c->partials; a.ticket = c->ticket;
     }
-    k_phys_residual<WRITE_R, REDUCE, SCALE><<<grid, 256, 0, st>>>(a);
+    if (c->exact_residuals) k_phys_residual<WRITE_R, REDUCE, SCALE, true><<<grid, 256, 0, st>>>(a);
+    else k_phys_residual<WRITE_R, REDUCE, SCALE, false><<<grid, 256, 0, st>>>(a);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -508,6 +521,12 @@ int physad_ctx_destroy(physad_ctx* c) {
 
 int physad_ctx_sm_count(const physad_ctx* c) { return c ? c->sm_count : 0; }
 uint64_t physad_launch_count(const physad_ctx* c) { return c ? c->launches : 0; }
+int physad_set_exact_residuals(physad_ctx* c, int on) {
+    if (!c) return -1;
+    const int prev = c->exact_residuals;
+    c->exact_residuals = on ? 1 : 0;
+    return prev;
+}
 int physad_set_fused_variant(physad_ctx* c, int v) {
     if (!c) return -1;
     const int prev = c->fused_variant;

@@ -28,6 +28,8 @@
 // Out-of-range columns of partial tiles evaluate at the wrapped/clamped coordinate, which is what
 // their in-range neighbours need as halo; they just never contribute to the sum.
 #pragma once
+#include <type_traits>
+
 #include "mlp_eval.cuh"
 
 namespace physad {
@@ -116,6 +118,7 @@ struct FusedArgs {
     const int* ranges;       // [gridDim.x + 1] block b owns tile-planes [ranges[b], ranges[b+1]) -- equal COST shares
     int m1p1, periodic;
     float inv2dt, inv2hx, inv2hy, inv2hz;
+    double inv2dt_d, inv2hx_d, inv2hy_d, inv2hz_d;  // 1.0/(2.0*double(h)): the exact-residual mode (DPRES)
     double2* partials;       // [gridDim.x]
     unsigned int* ticket;    // zero on entry, zero again on exit
     double* acc_out;         // [2]
@@ -204,7 +207,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     } while (!ok);
 }
 
-template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR = false>
+template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR = false, bool DPRES = false>
 __global__ void __launch_bounds__(32 * TYB, MINB)
 k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) {
     constexpr int TX = 32, TY = TYB * P, NWARPS = TYB;
@@ -255,18 +258,22 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
         cy[j] = __ldg(a.cys + bc_index(gy, a.ny, per));
         live[j] = gx < a.nx && gy < a.ny;
     }
-    float dT[P][4];  // time derivative of the plane whose residual is pending
+    // DPRES: derivatives and residual sums in double exactly as the CPU reference (bit-identical residuals)
+    using real = typename std::conditional<DPRES, double, float>::type;
+    const real i2t = DPRES ? real(a.inv2dt_d) : real(a.inv2dt), i2x = DPRES ? real(a.inv2hx_d) : real(a.inv2hx);
+    const real i2y = DPRES ? real(a.inv2hy_d) : real(a.inv2hy), i2z = DPRES ? real(a.inv2hz_d) : real(a.inv2hz);
+    real dT[P][4];  // time derivative of the plane whose residual is pending
 #pragma unroll
     for (int j = 0; j < P; ++j)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) dT[j][c] = 0.f;
+        for (int c = 0; c < 4; ++c) dT[j][c] = real(0);
 
     for (int k = 0; k <= nplanes + 1; ++k, ++kbuf) {
         const int zk = zc0 - 1 + k;
         const float cz = __ldg(a.czs + bc_index(zk, a.nz, per));
         float* pl = buf + (kbuf & (NB - 1)) * PLANE;
         const bool halo_plane = (k == 0) || (k == nplanes + 1);
-        float dTn[P][4];
+        real dTn[P][4];
         if (halo_plane) {
             float y[P][1][4];
             mlp_eval<H, 1, P, UNROLL, PACKED>(w, cx, cy, cz, y);
@@ -274,7 +281,7 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
             for (int j = 0; j < P; ++j) {
                 const int o = (1 + ty + j * TYB) * SX + 1 + tx;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { pl[c * CH + o] = y[j][0][c]; dTn[j][c] = 0.f; }
+                for (int c = 0; c < 4; ++c) { pl[c * CH + o] = y[j][0][c]; dTn[j][c] = real(0); }
             }
         } else {
             float y[P][3][4];
@@ -285,7 +292,7 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     pl[c * CH + o] = y[j][1][c];
-                    dTn[j][c] = central_diff(y[j][2][c], y[j][0][c], a.inv2dt);
+                    dTn[j][c] = central_diff(y[j][2][c], y[j][0][c], i2t);
                 }
             }
             // ring duty for this plane (x/y neighbours of the tile edge): NTASK tasks of 32 ring columns,
@@ -330,14 +337,15 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 const int o = (1 + ty + j * TYB) * SX + 1 + tx;
-                float f[4], gxv[4], gyv[4], gzv[4], R[4];
+                float f[4], R[4];
+                real gxv[4], gyv[4], gzv[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float* q = pc + c * CH + o;
                     f[c] = q[0];
-                    gxv[c] = central_diff(q[1], q[-1], a.inv2hx);
-                    gyv[c] = central_diff(q[SX], q[-SX], a.inv2hy);
-                    gzv[c] = central_diff(pp[c * CH + o], pm[c * CH + o], a.inv2hz);
+                    gxv[c] = central_diff(q[1], q[-1], i2x);
+                    gyv[c] = central_diff(q[SX], q[-SX], i2y);
+                    gzv[c] = central_diff(pp[c * CH + o], pm[c * CH + o], i2z);
                 }
                 point_residual(f, gxv, gyv, gzv, dT[j], R);
                 const float Rs = R[0], Rx = R[1], Ry = R[2], Rz = R[3];

@@ -188,14 +188,23 @@ __device__ __forceinline__ void mlp_eval(const MlpConst<H>& w, float cx, const f
 }
 
 // ---------------------------------------------------------------------------------------------
-// Point residual (reference src/phys_cpu.cpp:80-106), fp32 with every rounding spelled out so the
-// fused kernel and the stage-wise kernel produce identical bits from identical fields.
+// Point residual (reference src/phys_cpu.cpp:66-109), every rounding spelled out so the fused kernel and
+// the stage-wise kernel produce identical bits from identical fields.
 //   f = [sigma, ux, uy, uz] at the point;  g?[c] = d f_c / d?;  dT[c] = d f_c / dt.
-// The CPU reference evaluates the same expressions in double; fp32 with fused multiply-adds stays
-// within ~1e-7 * max|R| of it, well inside the 1e-5 gate.
+// Two arithmetic modes, selected by the type T of the derivatives:
+//   T = double : EXACTLY the CPU reference -- float loads widened to double, differences times
+//                1.0/(2.0*double(h)) (:38-41), sums in the order written on :96-106, separate multiply and
+//                add (the reference build does not contract), one rounding to float at the end.  Residuals
+//                are then bit-identical to cpu_phys_residuals.  Runs on the FP64 / conversion pipes, which
+//                the fp32-bound kernels leave idle.
+//   T = float  : the same expressions in fp32 with fused multiply-adds (what the reference's own CUDA
+//                kernels do, src/phys_cuda_fused.cu:67-99); within ~1e-7 * max|R| of the CPU.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float central_diff(float plus, float minus, float inv2h) {
     return __fmul_rn(__fsub_rn(plus, minus), inv2h);
+}
+__device__ __forceinline__ double central_diff(float plus, float minus, double inv2h) {
+    return __dmul_rn(__dsub_rn(double(plus), double(minus)), inv2h);
 }
 
 __device__ __forceinline__ void point_residual(const float (&f)[4], const float (&gx)[4], const float (&gy)[4],
@@ -207,6 +216,19 @@ __device__ __forceinline__ void point_residual(const float (&f)[4], const float 
         R[c] = __fadd_rn(dT[c], adv);
     }
     R[0] = __fmaf_rn(f[0], div, R[0]);
+}
+
+__device__ __forceinline__ void point_residual(const float (&f)[4], const double (&gx)[4], const double (&gy)[4],
+                                               const double (&gz)[4], const double (&dT)[4], float (&R)[4]) {
+    const double ux = double(f[1]), uy = double(f[2]), uz = double(f[3]);
+    const double div = __dadd_rn(__dadd_rn(gx[1], gy[2]), gz[3]);                                   // :96
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        // u.grad(f_c) = (ux*d/dx + uy*d/dy) + uz*d/dz                                                  :97-101
+        const double adv = __dadd_rn(__dadd_rn(__dmul_rn(ux, gx[c]), __dmul_rn(uy, gy[c])), __dmul_rn(uz, gz[c]));
+        const double r = __dadd_rn(dT[c], adv);
+        R[c] = float(c == 0 ? __dadd_rn(r, __dmul_rn(double(f[0]), div)) : r);                      // :103-106
+    }
 }
 
 }  // namespace physad

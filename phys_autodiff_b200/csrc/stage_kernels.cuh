@@ -210,6 +210,7 @@ struct PhysArgs {
     int periodic;
     int zc;  // planes per z chunk
     float inv2dt, inv2hx, inv2hy, inv2hz;
+    double inv2dt_d, inv2hx_d, inv2hy_d, inv2hz_d;  // exact-residual mode (DPRES)
     float scale_s, scale_u;
     const float* s_m; const float* s_0; const float* s_p;
     const float* u_m; const float* u_0; const float* u_p;
@@ -223,8 +224,11 @@ __device__ __forceinline__ int nb1(int v, int n, bool periodic) {
     return v < 0 ? 0 : (v >= n ? n - 1 : v);
 }
 
-template <bool WRITE_R, bool REDUCE, bool SCALE>
+template <bool WRITE_R, bool REDUCE, bool SCALE, bool DPRES>
 __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
+    using real = typename std::conditional<DPRES, double, float>::type;
+    const real i2t = DPRES ? real(a.inv2dt_d) : real(a.inv2dt), i2x = DPRES ? real(a.inv2hx_d) : real(a.inv2hx);
+    const real i2y = DPRES ? real(a.inv2hy_d) : real(a.inv2hy), i2z = DPRES ? real(a.inv2hz_d) : real(a.inv2hz);
     __shared__ double2 s_red[8];
     __shared__ unsigned int s_flag;
     const bool per = a.periodic != 0;
@@ -264,13 +268,14 @@ __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
             for (int c = 0; c < 4; ++c) {
                 ntp[c] = __ldg(fp[c] + pzn); ntm[c] = __ldg(fm[c] + pzn); nhi[c] = __ldg(f0[c] + pzn2);
             }
-            float dT[4], gx[4], gy[4], gz[4], R[4];
+            real dT[4], gx[4], gy[4], gz[4];
+            float R[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                dT[c] = central_diff(tp[c], tm[c], a.inv2dt);
-                gx[c] = central_diff(__ldg(f0[c] + pz + oxp), __ldg(f0[c] + pz + oxm), a.inv2hx);
-                gy[c] = central_diff(__ldg(f0[c] + pz + oyp), __ldg(f0[c] + pz + oym), a.inv2hy);
-                gz[c] = central_diff(hi[c], lo[c], a.inv2hz);
+                dT[c] = central_diff(tp[c], tm[c], i2t);
+                gx[c] = central_diff(__ldg(f0[c] + pz + oxp), __ldg(f0[c] + pz + oxm), i2x);
+                gy[c] = central_diff(__ldg(f0[c] + pz + oyp), __ldg(f0[c] + pz + oym), i2y);
+                gz[c] = central_diff(hi[c], lo[c], i2z);
             }
             point_residual(mid, gx, gy, gz, dT, R);
             if (WRITE_R) {

@@ -60,6 +60,11 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.physad_launch_count(self._h))
 
+    def set_exact_residuals(self, on: bool) -> bool:
+        """False (default): residual arithmetic in fp32 with FMAs like the reference's own CUDA kernels;
+        True: in double exactly as the CPU reference (bit-identical residuals, ~5 % slower)."""
+        return bool(self._lib.physad_set_exact_residuals(self._h, C.c_int(int(on))))
+
     def set_fused_variant(self, v: int) -> int:
         return int(self._lib.physad_set_fused_variant(self._h, C.c_int(v)))
 

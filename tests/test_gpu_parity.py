@@ -259,6 +259,26 @@ def test_fused_loss_vs_cpu(ctx, checker, shape, H, per, m1p1, h, dt):
     assert l2[0] == got[0] and l2[1] == got[1]
 
 
+@pytest.mark.parametrize("shape,H,per,m1p1,h,dt", FUSED_CASES[:6])
+def test_exact_residual_mode_is_bit_identical_to_cpu(ctx, checker, shape, H, per, m1p1, h, dt):
+    """physad_set_exact_residuals(1): stencil + residual sums in double exactly as src/phys_cpu.cpp:66-109, so
+    the fused kernel's and the stage-wise kernel's residuals equal the CPU reference BITWISE."""
+    og = OGrid(*shape, *h, dt, per)
+    w = checker.mlp_random_init(H, 777, 0.25)
+    f = checker.generate_fields(og, w, 0.25, dt, m1p1)
+    ls, lu, R = checker.phys_loss_forward(og, 1.3, 0.7, f, True)
+    ctx.set_exact_residuals(True)
+    try:
+        got = ctx.fused_loss_host(_g(og), _cfg(H, m1p1), *w, _pw(1.3, 0.7), 0.25, dt, want_residuals=True)
+        staged = ctx.phys_loss_host(_g(og), _pw(1.3, 0.7), f, want_residuals=True)
+    finally:
+        ctx.set_exact_residuals(False)
+    for a, b, c in zip(got[2], staged[2], R):
+        assert bits_equal(a, c) and bits_equal(b, c)
+    for out in (got, staged):  # identical residuals: only the order of the double additions differs
+        assert abs(out[0] - ls) <= 1e-6 * abs(ls) + 1e-30 and abs(out[1] - lu) <= 1e-6 * abs(lu) + 1e-30
+
+
 def test_fused_loss_anchors(ctx, golden, checker):
     _, meta = golden
     from phys_autodiff_b200 import Grid
