@@ -405,6 +405,30 @@ int launch_phys(physad_ctx* c, const physad_grid* g, PhysArgs a, cudaStream_t st
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.periodic = g->periodic != 0;
     a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
     a.inv2dt_d = inv2d(g->dt); a.inv2hx_d = inv2d(g->hx); a.inv2hy_d = inv2d(g->hy); a.inv2hz_d = inv2d(g->hz);
+    // 128-bit form when rows are quad-aligned and wide enough to fill the 64-quad blocks reasonably
+    static const bool no_v4 = getenv("PHYSAD_NO_V4") != nullptr;  // tuning aid
+    bool v4 = !no_v4 && g->nx % 4 == 0 && g->nx >= 128;
+    const void* ptrs[10] = {a.s_m, a.s_0, a.s_p, a.u_m, a.u_0, a.u_p, a.R[0], a.R[1], a.R[2], a.R[3]};
+    for (const void* p : ptrs) v4 = v4 && (uintptr_t(p) % 16 == 0);
+    if (v4) {
+        const unsigned tx = unsigned((g->nx + 255) / 256), ty = unsigned((g->ny + 3) / 4);
+        if (ty > 65535u) return fail(PHYSAD_E_UNSUPPORTED, "phys kernels: ny > 262140");
+        const long long want = (long long)c->sm_count * 8;
+        long long nch = std::max(1LL, std::min<long long>(g->nz, (want + (long long)tx * ty - 1) / ((long long)tx * ty)));
+        a.zc = int((g->nz + nch - 1) / nch);
+        nch = (g->nz + a.zc - 1) / a.zc;
+        if (nch > 65535) { a.zc = (g->nz + 65534) / 65535; nch = (g->nz + a.zc - 1) / a.zc; }
+        const dim3 grid(tx, ty, unsigned(nch));
+        if (REDUCE) {
+            if (int rc = ensure_partials(c, size_t(tx) * ty * nch)) return rc;
+            a.partials = c->partials; a.ticket = c->ticket;
+        }
+        if (c->exact_residuals) k_phys_residual_v4<WRITE_R, REDUCE, SCALE, true><<<grid, 256, 0, st>>>(a);
+        else k_phys_residual_v4<WRITE_R, REDUCE, SCALE, false><<<grid, 256, 0, st>>>(a);
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     // 32 x 8 column tiles, each marching a z chunk; enough chunks for ~16 blocks per SM
     const unsigned tx = unsigned((g->nx + 31) / 32), ty = unsigned((g->ny + 7) / 8);
     if (ty > 65535u) return fail(PHYSAD_E_UNSUPPORTED, "phys kernels: ny > 524280");
