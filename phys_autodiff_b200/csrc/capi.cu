@@ -303,38 +303,41 @@ int launch_fused_d(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
     return 0;
 }
 
+// fp32-residual launch of a given geometry (all tuning variants)
 template <int H, int P, int TYB, int UNROLL, int MINB, bool PACKED, bool SPLITBAR = false>
 int launch_fused_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool xchg, double* acc,
                    float* const R[4], cudaStream_t st, int blocks_per_sm_cap = 0) {
-    if (c->exact_residuals)
-        return launch_fused_d<H, P, TYB, UNROLL, MINB, PACKED, SPLITBAR, true>(c, g, s, tc, xchg, acc, R, st, blocks_per_sm_cap);
     return launch_fused_d<H, P, TYB, UNROLL, MINB, PACKED, SPLITBAR, false>(c, g, s, tc, xchg, acc, R, st, blocks_per_sm_cap);
+}
+
+// The default geometry: one 512-thread block/SM on 32x64 tiles; for small slabs (multi-GPU strong scaling: a block's
+// share is only a few planes, and every z-segment costs ~1.15 plane-steps of halo + prologue) one 256-thread
+// block/SM on 32x32 tiles, which halves the number of z-segments (measured 0.1626 vs 0.1668 ms on 256x256x32).
+template <int H, bool DPRES>
+int launch_fused_default(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool xchg,
+                         double* acc, float* const R[4], cudaStream_t st) {
+    const long long tile_planes = (long long)((g->nx + 31) / 32) * ((g->ny + 63) / 64) * (s.z_end - s.z_begin);
+    if (tile_planes < 12LL * c->sm_count)
+        return launch_fused_d<H, 4, 8, 2, 2, true, true, DPRES>(c, g, s, tc, xchg, acc, R, st, 1);
+    return launch_fused_d<H, 4, 16, 2, 1, true, true, DPRES>(c, g, s, tc, xchg, acc, R, st, 0);
 }
 
 template <int H>
 int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], bool dt, double* acc,
                    float* const R[4], cudaStream_t st) {
+    // exact (double) residual arithmetic is built for the default geometry only
+    if (c->exact_residuals) return launch_fused_default<H, true>(c, g, s, tc, dt, acc, R, st);
     // <H, P columns/thread, warps/block, unroll (pairs of hidden units), min blocks/SM, packed, split barrier>
     switch (c->fused_variant) {
         default:
-        case 0: {
-            // Small slabs (multi-GPU strong scaling): a block's share is only a few planes, and every z-segment
-            // costs ~1.15 plane-steps of halo + prologue.  Halving the columns in flight per SM (one 256-thread
-            // block) doubles the segment length; measured 0.1765 vs 0.1866 ms for a 256x256x32 slab.
-            const long long tile_planes = (long long)((g->nx + 31) / 32) * ((g->ny + 63) / 64) * (s.z_end - s.z_begin);
-            if (tile_planes < 12LL * c->sm_count)
-                return launch_fused_t<H, 4, 8, 2, 2, true, true>(c, g, s, tc, dt, acc, R, st, 1);
-            return launch_fused_t<H, 4, 16, 2, 1, true, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x64, 1 x 512 threads/SM
-        }
+        case 0: return launch_fused_default<H, false>(c, g, s, tc, dt, acc, R, st);
         case 1: return launch_fused_t<H, 4, 8, 2, 2, true, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x32, 2 x 256 threads/SM
         case 2: return launch_fused_t<H, 4, 16, 2, 1, true, false>(c, g, s, tc, dt, acc, R, st);  // variant 0 with __syncthreads
         case 3: return launch_fused_t<H, 4, 8, 2, 1, false, false>(c, g, s, tc, dt, acc, R, st);  // scalar FMUL/FADD cross-check
         case 4: return launch_fused_t<H, 2, 16, 4, 1, true, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x32, 1 x 512
         case 5: return launch_fused_t<H, 1, 8, 4, 4, true, false>(c, g, s, tc, dt, acc, R, st);   // tile 32x8
         case 6: return launch_fused_t<H, 2, 8, 2, 3, true, true>(c, g, s, tc, dt, acc, R, st);    // tile 32x16, 3 x 256
-        case 7: return launch_fused_t<H, 4, 8, 2, 2, true, false>(c, g, s, tc, dt, acc, R, st);   // variant 1 with __syncthreads
-        case 8: return launch_fused_t<H, 1, 16, 4, 2, true, true>(c, g, s, tc, dt, acc, R, st);   // tile 32x16, 512 threads
-        case 9: return launch_fused_t<H, 4, 8, 2, 2, true, true>(c, g, s, tc, dt, acc, R, st, 1); // tile 32x32, ONE 256-thread block/SM
+        case 7: return launch_fused_t<H, 4, 8, 2, 2, true, true>(c, g, s, tc, dt, acc, R, st, 1); // tile 32x32, ONE 256-thread block/SM
     }
 }
 

@@ -290,7 +290,7 @@ def test_fused_loss_anchors(ctx, golden, checker):
         assert abs(lu - float(a["loss_u"])) <= TOL_LOSS * float(a["loss_u"])
 
 
-@pytest.mark.parametrize("variant", list(range(10)))
+@pytest.mark.parametrize("variant", list(range(8)))
 def test_fused_variants_agree(ctx, checker, variant):
     """Every launch geometry of the fused kernel gives the same residuals (bitwise) and loss."""
     og = OGrid(70, 37, 9, 1, 1, 1, 2e-3, True)
