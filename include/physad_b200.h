@@ -144,6 +144,17 @@ int physad_phys_loss_host(physad_ctx* ctx, const physad_grid* g, const physad_ph
                           const float* u_tp1, float* loss_sigma, float* loss_u, float* R_sigma, float* R_ux,
                           float* R_uy, float* R_uz);
 
+/* The same on one rank's z-slab of supplied fields (multi-GPU): the six arrays
+ * hold only the slab's planes (sigma_*: n, u_*: 3n channel-major, n = slab points); halo_lo / halo_hi
+ * ([4 channels: sigma_t, ux_t, uy_t, uz_t][ny][nx] each, device) are the time-t planes just below / above the
+ * slab in the GLOBAL grid with the wrap/clamp rule already applied -- the host obtains them from the
+ * neighbouring ranks (ops.Context.phys_loss_sharded all-gathers the boundary planes with torch.distributed).
+ * acc_dev[2] receives this slab's sums; R_* (slab-local) may be NULL. */
+int physad_phys_loss_slab_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, const float* sigma_tm1,
+                              const float* sigma_t, const float* sigma_tp1, const float* u_tm1, const float* u_t,
+                              const float* u_tp1, const float* halo_lo, const float* halo_hi, double* acc_dev,
+                              float* R_sigma, float* R_ux, float* R_uy, float* R_uz, void* stream);
+
 /* Residual VJP g = (2 w / float(N)) R.  Replaces cuda_phys_loss_backward_nonfused
  * (include/phys.h:94-103; CPU: src/phys_cpu.cpp:151-170). */
 int physad_phys_backward_dev(physad_ctx* ctx, const physad_grid* g, const physad_phys_weights* w, const float* R_sigma,

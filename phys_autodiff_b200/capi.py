@@ -85,7 +85,7 @@ EXPORTS = [
     "physad_mlp_grid_infer_dev", "physad_mlp_grid_infer_host",
     "physad_mlp_generate_fields_dev", "physad_mlp_generate_fields_host",
     "physad_phys_residuals_dev", "physad_phys_residuals_host",
-    "physad_phys_loss_dev", "physad_phys_loss_host",
+    "physad_phys_loss_dev", "physad_phys_loss_host", "physad_phys_loss_slab_dev",
     "physad_phys_backward_dev", "physad_phys_backward_host",
     "physad_phys_backward_from_fields_dev", "physad_phys_backward_from_fields_host",
     "physad_fused_loss_dev", "physad_fused_loss_host", "physad_fused_loss_slab_host", "physad_finalize_loss",

@@ -404,15 +404,24 @@ int launch_grid(physad_ctx* c, const physad_grid* g, const physad_slab& s, const
 
 // ---- physics on supplied fields --------------------------------------------------------------
 template <bool WRITE_R, bool REDUCE, bool SCALE>
-int launch_phys(physad_ctx* c, const physad_grid* g, PhysArgs a, cudaStream_t st) {
+int launch_phys(physad_ctx* c, const physad_grid* g_in, PhysArgs a, cudaStream_t st, int slab_planes = -1) {
+    // slab mode: the arrays hold `slab_planes` planes and the z neighbours outside them come from a.halo_lo/hi
+    physad_grid gl = *g_in;
+    if (slab_planes >= 0) gl.nz = slab_planes;
+    const physad_grid* g = &gl;
+    if (g->nz == 0) {
+        if (REDUCE) CU(cudaMemsetAsync(a.acc_out, 0, 2 * sizeof(double), st));
+        return 0;
+    }
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.periodic = g->periodic != 0;
     a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
     a.inv2dt_d = inv2d(g->dt); a.inv2hx_d = inv2d(g->hx); a.inv2hy_d = inv2d(g->hy); a.inv2hz_d = inv2d(g->hz);
     // 128-bit form when rows are quad-aligned and wide enough to fill the 64-quad blocks reasonably
     static const bool no_v4 = getenv("PHYSAD_NO_V4") != nullptr;  // tuning aid
     bool v4 = !no_v4 && g->nx % 4 == 0 && g->nx >= 128;
-    const void* ptrs[10] = {a.s_m, a.s_0, a.s_p, a.u_m, a.u_0, a.u_p, a.R[0], a.R[1], a.R[2], a.R[3]};
+    const void* ptrs[12] = {a.s_m, a.s_0, a.s_p, a.u_m, a.u_0, a.u_p, a.R[0], a.R[1], a.R[2], a.R[3], a.halo_lo, a.halo_hi};
     for (const void* p : ptrs) v4 = v4 && (uintptr_t(p) % 16 == 0);
+    v4 = v4 && (size_t(g->nx) * g->ny * g->nz) % 4 == 0;  // channel stride of the u arrays
     if (v4) {
         const unsigned tx = unsigned((g->nx + 255) / 256), ty = unsigned((g->ny + 3) / 4);
         if (ty > 65535u) return fail(PHYSAD_E_UNSUPPORTED, "phys kernels: ny > 262140");
@@ -781,6 +790,25 @@ int physad_phys_loss_dev(physad_ctx* c, const physad_grid* g, const float* s_m, 
     a.acc_out = acc;
     if (Rs || Rx || Ry || Rz) return launch_phys<true, true, false>(c, g, a, cudaStream_t(stream));
     return launch_phys<false, true, false>(c, g, a, cudaStream_t(stream));
+}
+
+int physad_phys_loss_slab_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, const float* s_m,
+                              const float* s_0, const float* s_p, const float* u_m, const float* u_0, const float* u_p,
+                              const float* halo_lo, const float* halo_hi, double* acc, float* Rs, float* Rx, float* Ry,
+                              float* Rz, void* stream) {
+    if (!c || !slab || !acc) return fail(PHYSAD_E_INVALID, "phys_loss_slab: null argument");
+    if (int rc = check_grid(g)) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    const int nzl = s.z_end - s.z_begin;
+    if (nzl > 0 && (!s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p || !halo_lo || !halo_hi))
+        return fail(PHYSAD_E_INVALID, "phys_loss_slab: null field or halo pointer");
+    DeviceGuard dg(c->device);
+    PhysArgs a = phys_args(s_m, s_0, s_p, u_m, u_0, u_p, Rs, Rx, Ry, Rz);
+    a.acc_out = acc;
+    a.halo_lo = halo_lo; a.halo_hi = halo_hi;
+    if (Rs || Rx || Ry || Rz) return launch_phys<true, true, false>(c, g, a, cudaStream_t(stream), nzl);
+    return launch_phys<false, true, false>(c, g, a, cudaStream_t(stream), nzl);
 }
 
 int physad_phys_backward_dev(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w, const float* Rs,

@@ -206,9 +206,14 @@ __global__ void __launch_bounds__(256) k_bwd_db(const float* __restrict__ G, flo
 //             cuda_phys_loss_backward_fused, include/phys.h:132-143)
 // ---------------------------------------------------------------------------------------------
 struct PhysArgs {
-    int nx, ny, nz;
+    int nx, ny, nz;   // nz = number of planes IN THE ARRAYS (the slab's planes in slab mode)
     int periodic;
     int zc;  // planes per z chunk
+    // slab mode (multi-GPU on supplied fields): the arrays hold only this rank's planes, and the time-t planes
+    // just below / above the slab ([4 channels][ny][nx] each, already wrapped/clamped by the host) come from
+    // these two buffers.  Null = whole grid in the arrays, wrap/clamp inside them.
+    const float* halo_lo;
+    const float* halo_hi;
     float inv2dt, inv2hx, inv2hy, inv2hz;
     double inv2dt_d, inv2hx_d, inv2hy_d, inv2hz_d;  // exact-residual mode (DPRES)
     float scale_s, scale_u;
@@ -217,6 +222,18 @@ struct PhysArgs {
     float* R[4];
     double2* partials; unsigned int* ticket; double* acc_out;
 };
+
+// time-t plane just below / above plane z of channel c (see PhysArgs::halo_lo/hi)
+__device__ __forceinline__ const float* plane_below(const PhysArgs& a, const float* f0c, int c, int z, size_t pln, bool per) {
+    if (z > 0) return f0c + size_t(z - 1) * pln;
+    if (a.halo_lo) return a.halo_lo + size_t(c) * pln;
+    return f0c + size_t(per ? a.nz - 1 : 0) * pln;
+}
+__device__ __forceinline__ const float* plane_above(const PhysArgs& a, const float* f0c, int c, int z, size_t pln, bool per) {
+    if (z + 1 < a.nz) return f0c + size_t(z + 1) * pln;
+    if (a.halo_hi) return a.halo_hi + size_t(c) * pln;
+    return f0c + size_t(per ? 0 : a.nz - 1) * pln;
+}
 
 // neighbour index for an offset of +-1 (n >= 1): wrap or clamp without a division
 __device__ __forceinline__ int nb1(int v, int n, bool periodic) {
@@ -250,11 +267,12 @@ __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
         float lo[4], mid[4], hi[4];      // time-t values at z-1, z, z+1 of this column
         float tp[4], tm[4];              // t+dt / t-dt values at z
         {
-            const size_t pm = size_t(nb1(z0 - 1, a.nz, per)) * pln + oc, pc = size_t(z0) * pln + oc;
-            const size_t pn = size_t(nb1(z0 + 1, a.nz, per)) * pln + oc;
+            const size_t pc = size_t(z0) * pln + oc;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                lo[c] = __ldg(f0[c] + pm); mid[c] = __ldg(f0[c] + pc); hi[c] = __ldg(f0[c] + pn);
+                lo[c] = __ldg(plane_below(a, f0[c], c, z0, pln, per) + oc);
+                mid[c] = __ldg(f0[c] + pc);
+                hi[c] = __ldg(plane_above(a, f0[c], c, z0, pln, per) + oc);
                 tp[c] = __ldg(fp[c] + pc); tm[c] = __ldg(fm[c] + pc);
             }
         }
@@ -262,11 +280,12 @@ __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
             const size_t pz = size_t(z) * pln;
             // prefetch for the next iteration (plane z+1's t+-dt values, plane z+2's time-t value)
             const int zn = min(z + 1, a.nz - 1);  // clamped only to stay in bounds on the last iteration
-            const size_t pzn = size_t(zn) * pln + oc, pzn2 = size_t(nb1(zn + 1, a.nz, per)) * pln + oc;
+            const size_t pzn = size_t(zn) * pln + oc;
             float ntp[4], ntm[4], nhi[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                ntp[c] = __ldg(fp[c] + pzn); ntm[c] = __ldg(fm[c] + pzn); nhi[c] = __ldg(f0[c] + pzn2);
+                ntp[c] = __ldg(fp[c] + pzn); ntm[c] = __ldg(fm[c] + pzn);
+                nhi[c] = __ldg(plane_above(a, f0[c], c, zn, pln, per) + oc);
             }
             real dT[4], gx[4], gy[4], gz[4];
             float R[4];
@@ -333,17 +352,17 @@ __global__ void __launch_bounds__(256) k_phys_residual_v4(const PhysArgs a) {
         const float* fp[4] = {a.s_p, a.u_p, a.u_p + N, a.u_p + 2 * N};
         float4 lo[4], mid[4], hi[4];
         {
-            const size_t pm = size_t(nb1(z0 - 1, a.nz, per)) * pln + oc, pc = size_t(z0) * pln + oc;
+            const size_t pc = size_t(z0) * pln + oc;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { lo[c] = ldg4(f0[c] + pm); mid[c] = ldg4(f0[c] + pc); }
+            for (int c = 0; c < 4; ++c) { lo[c] = ldg4(plane_below(a, f0[c], c, z0, pln, per) + oc); mid[c] = ldg4(f0[c] + pc); }
         }
         for (int z = z0; z < z1; ++z) {
-            const size_t pz = size_t(z) * pln, pzp = size_t(nb1(z + 1, a.nz, per)) * pln;
+            const size_t pz = size_t(z) * pln;
             float4 tp[4], tm[4], yp[4], ym[4];
             float xl[4], xr[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                hi[c] = ldg4(f0[c] + pzp + oc);
+                hi[c] = ldg4(plane_above(a, f0[c], c, z, pln, per) + oc);
                 tp[c] = ldg4(fp[c] + pz + oc);
                 tm[c] = ldg4(fm[c] + pz + oc);
                 yp[c] = ldg4(f0[c] + pz + oyp);

@@ -162,6 +162,73 @@ class Context:
         ls, lu = self.finalize(acc.cpu().numpy(), pw, g.N)
         return (ls, lu, out[1]) if want_residuals else (ls, lu)
 
+    def phys_loss_slab_acc(self, g: Grid, slab, fields_local: Sequence, halo_lo, halo_hi, want_residuals: bool = False):
+        """One rank's share of the loss on supplied fields: `fields_local` hold the slab's planes, `halo_lo/hi`
+        ([4, ny, nx] float32 device tensors) the time-t planes below / above it.  Returns the device sums."""
+        import torch
+        cs, n = self._slab(g, slab)
+        acc = self._empty(2, torch.float64)
+        R = [self._empty(n) for _ in range(4)] if want_residuals else [None] * 4
+        cg = g.c()
+        check(self._lib.physad_phys_loss_slab_dev(self._h, C.byref(cg), C.byref(cs), *[ptr(f) for f in fields_local],
+                                                  ptr(halo_lo), ptr(halo_hi), ptr(acc), *[ptr(r) for r in R],
+                                                  self._stream()), "phys_loss_slab")
+        return (acc, tuple(R)) if want_residuals else acc
+
+    @staticmethod
+    def halo_sources(g: Grid, slab):
+        """Global plane indices (wrap/clamp applied) a slab needs below and above itself."""
+        z0, z1 = slab
+        if g.periodic:
+            return (z0 - 1) % g.nz, z1 % g.nz
+        return max(z0 - 1, 0), min(z1, g.nz - 1)
+
+    def phys_loss_sharded(self, g: Grid, pw: PhysWeights, fields_local: Sequence, group=None, want_residuals: bool = False):
+        """Multi-GPU loss on externally supplied, z-sharded fields: every rank holds its slab of the six fields;
+        the two time-t boundary planes of every slab are all-gathered (2 x 4 x ny x nx floats per rank), each
+        rank picks its two halo planes, runs the stencil + reduction on its slab, and one all-reduce of two
+        doubles combines the sums."""
+        import torch
+        import torch.distributed as dist
+        world, rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_initialized() else (1, 0)
+        slabs = [slab_for_rank(g.nz, r, world) for r in range(world)]
+        z0, z1 = slabs[rank]
+        pln = g.nx * g.ny
+        s_0, u_0 = fields_local[1], fields_local[4]
+        n = (z1 - z0) * pln
+
+        def plane(zl):  # [4, pln]: sigma_t, ux_t, uy_t, uz_t of local plane zl
+            return torch.stack([s_0[zl * pln:(zl + 1) * pln]] + [u_0[c * n + zl * pln: c * n + (zl + 1) * pln] for c in range(3)])
+        mine = torch.stack([plane(0), plane(z1 - z0 - 1)]) if z1 > z0 else torch.zeros(2, 4, pln, device="cuda")
+        if world > 1:
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine.contiguous(), group=group)
+        else:
+            gathered = [mine]
+        lo_z, hi_z = self.halo_sources(g, (z0, z1))
+
+        def fetch(zg):  # boundary plane zg is the first or the last plane of its owner's slab
+            owner = next(r for r, (a, b) in enumerate(slabs) if a <= zg < b)
+            a, b = slabs[owner]
+            if zg == a:
+                return gathered[owner][0]
+            if zg == b - 1:
+                return gathered[owner][1]
+            raise capi.PhysadError("halo plane is not a slab boundary plane (slab thinner than the stencil?)")
+        if z1 > z0:
+            # planes inside my own slab (single rank, or clamp at the domain edge) come from my own arrays
+            halo_lo = plane(lo_z - z0) if z0 <= lo_z < z1 else fetch(lo_z)
+            halo_hi = plane(hi_z - z0) if z0 <= hi_z < z1 else fetch(hi_z)
+            out = self.phys_loss_slab_acc(g, (z0, z1), fields_local, halo_lo.contiguous(), halo_hi.contiguous(), want_residuals)
+        else:
+            out = (torch.zeros(2, dtype=torch.float64, device="cuda"), tuple([self._empty(0)] * 4)) if want_residuals \
+                else torch.zeros(2, dtype=torch.float64, device="cuda")
+        acc = out[0] if want_residuals else out
+        if world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        ls, lu = self.finalize(self._read_acc(acc), pw, g.N)
+        return (ls, lu, out[1]) if want_residuals else (ls, lu)
+
     def phys_backward(self, g: Grid, pw: PhysWeights, R: Sequence):
         G = [self._empty(g.N) for _ in range(4)]
         cg, cw = g.c(), pw.c()

@@ -198,6 +198,43 @@ def test_residuals_random_fields(ctx, checker, shape, per):
         assert max_rel_to_max(a, b) <= TOL_FIELD
 
 
+@pytest.mark.parametrize("shape,per", [((128, 96, 40), True), ((128, 96, 40), False), ((33, 18, 7), True), ((36, 10, 3), False)])
+def test_stagewise_slabs_with_halo_planes(ctx, shape, per):
+    """Multi-GPU arithmetic of the stage-wise path on one GPU: the fields cut into 1/2/3/5 z-slabs, every slab given
+    its two halo planes (wrap / clamp applied), reproduces the whole-grid residuals bitwise and the sums."""
+    import torch
+    from phys_autodiff_b200 import Grid
+    from phys_autodiff_b200.ops import slab_for_rank
+    rng = np.random.default_rng(11)
+    g = Grid(*shape, 0.7, 1.3, 0.9, 3e-3, per)
+    N, pln = g.N, g.nx * g.ny
+    f = [_t(rng.standard_normal(N).astype(np.float32)) for _ in range(3)] + \
+        [_t(rng.standard_normal(3 * N).astype(np.float32)) for _ in range(3)]
+    acc_w, Rw = ctx.phys_loss_acc(g, f, want_residuals=True)
+    acc_w = acc_w.cpu().numpy()
+
+    def planes(a, z0, z1, vec):  # slab-local copy of a scalar / channel-major vector field
+        if not vec:
+            return a[z0 * pln:z1 * pln].contiguous()
+        return torch.cat([a[c * N + z0 * pln: c * N + z1 * pln] for c in range(3)]).contiguous()
+
+    def tplane(z):  # [4, pln] time-t plane z of the global fields
+        return torch.stack([f[1][z * pln:(z + 1) * pln]] + [f[4][c * N + z * pln: c * N + (z + 1) * pln] for c in range(3)]).contiguous()
+    for world in (1, 2, 3, 5):
+        tot = np.zeros(2)
+        for r in range(world):
+            z0, z1 = slab_for_rank(g.nz, r, world)
+            if z1 == z0:
+                continue
+            loc = [planes(f[k], z0, z1, k >= 3) for k in range(6)]
+            lo_z, hi_z = ctx.halo_sources(g, (z0, z1))
+            acc, R = ctx.phys_loss_slab_acc(g, (z0, z1), loc, tplane(lo_z), tplane(hi_z), want_residuals=True)
+            tot += acc.cpu().numpy()
+            for a, b in zip(R, Rw):
+                assert torch.equal(a, b[z0 * pln:z1 * pln]), (world, r)
+        assert np.allclose(tot, acc_w, rtol=1e-12)
+
+
 def test_golden_path_cases(ctx, golden):
     """Committed golden vectors (generated from the reference) through every stage on the GPU."""
     from phys_autodiff_b200 import Grid

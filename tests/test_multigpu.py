@@ -29,6 +29,10 @@ host_step = ctx.prepare_step_host(g, MLPConfig(4, 64, 4, True), *w, PhysWeights(
                                   slab=ops.slab_for_rank(g.nz, rank, world))
 p2p += [host_step() for _ in range(3)]                                                     # one-call host form
 ctx.disconnect_peers()
+# stage-wise path on z-sharded, externally supplied fields: every rank generates only ITS slab of the six fields,
+# boundary planes are all-gathered, stencil + reduction per slab, one all-reduce
+fl = ctx.mlp_generate_fields(g, 0.25, 2e-3, slab=ops.slab_for_rank(g.nz, rank, world))
+sh = ctx.phys_loss_sharded(g, PhysWeights(1.3, 0.7), fl, want_residuals=True)
 z0, z1 = ops.slab_for_rank(g.nz, rank, world)
 # single-GPU answer for the same grid on this rank's device (no process group involved)
 whole = ctx.fused_loss_acc(g, 0.25, 2e-3).cpu().numpy()
@@ -36,8 +40,9 @@ Rw = [torch.empty(g.N, device="cuda") for _ in range(4)]
 ctx.fused_loss_acc(g, 0.25, 2e-3, residuals=Rw)
 plane = g.nx * g.ny
 same = all(torch.equal(a, b[z0 * plane:z1 * plane]) for a, b in zip(R, Rw))
+same = same and all(torch.equal(a, b[z0 * plane:z1 * plane]) for a, b in zip(sh[2], Rw))
 l1 = ctx.finalize(whole, PhysWeights(1.3, 0.7), g.N)
-out = dict(rank=rank, p2p=[[float(a), float(b)] for a, b in p2p], ls=float(ls), lu=float(lu), ls1=float(l1[0]), lu1=float(l1[1]), same=bool(same), slab=[z0, z1])
+out = dict(rank=rank, sharded=[float(sh[0]), float(sh[1])], p2p=[[float(a), float(b)] for a, b in p2p], ls=float(ls), lu=float(lu), ls1=float(l1[0]), lu1=float(l1[1]), same=bool(same), slab=[z0, z1])
 gathered = [None] * world
 dist.all_gather_object(gathered, out)
 if rank == 0:
@@ -66,5 +71,7 @@ def test_two_rank_fused_loss_matches_single_gpu(tmp_path):
         # peer-memory exchange: same value on every rank and every epoch, and equal to the NCCL result
         # up to the order of the additions (rank order vs NCCL's)
         assert all(p == res[0]["p2p"][0] for p in d["p2p"]), d["p2p"]
+        assert d["sharded"] == res[0]["sharded"]
+        assert abs(d["sharded"][0] - d["ls1"]) <= 1e-6 * abs(d["ls1"]) and abs(d["sharded"][1] - d["lu1"]) <= 1e-6 * abs(d["lu1"])
         assert abs(d["p2p"][0][0] - d["ls"]) <= 1e-6 * abs(d["ls"]) and abs(d["p2p"][0][1] - d["lu"]) <= 1e-6 * abs(d["lu"])
         assert abs(d["ls"] - d["ls1"]) <= 1e-6 * abs(d["ls1"]) and abs(d["lu"] - d["lu1"]) <= 1e-6 * abs(d["lu1"])
