@@ -291,19 +291,9 @@ def main():
 
     # multi-GPU: the two partial sums are all-reduced inside the kernel over NVLink peer memory unless
     # --collective nccl asks for the plain kernel + one NCCL all-reduce of 2 doubles
-    p2p = False
-    if world > 1 and args.collective == "p2p":
-        try:
-            ok = ctx.connect_peers()
-        except Exception as e:  # CUDA IPC unavailable (e.g. restricted container): every rank falls back to NCCL
-            ok = False
-            if rank == 0:
-                print(f"bench: peer-memory exchange unavailable ({e}); using NCCL all-reduce", file=sys.stderr)
-        flag = torch.tensor([1 if ok else 0], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        p2p = bool(flag.item())
-        if not p2p and ok:
-            ctx.disconnect_peers()
+    p2p = world > 1 and args.collective == "p2p" and ctx.connect_peers()   # False on every rank if CUDA IPC is unavailable
+    if world > 1 and args.collective == "p2p" and not p2p and rank == 0:
+        print("bench: peer-memory exchange unavailable; using the NCCL all-reduce", file=sys.stderr)
     launch = ctx.prepare_fused(g, T0, DT, slab=slab, acc=acc, allreduce=bool(p2p))   # pre-marshalled C-ABI call
 
     def step():

@@ -71,18 +71,28 @@ class Context:
     def connect_peers(self, group=None) -> bool:
         """Map every rank's exchange buffer (CUDA IPC over NVLink) so the fused kernel can all-reduce its
         two sums itself.  torch.distributed is used only to all-gather the 64-byte handles.  Returns
-        False (and leaves the NCCL path in place) for a single rank."""
+        False (and leaves the NCCL path in place) for a single rank, or -- consistently on every rank --
+        when any rank could not export or map a buffer (e.g. CUDA IPC not permitted in the container)."""
+        import torch
         import torch.distributed as dist
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return False
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         buf = C.create_string_buffer(64)
-        check(self._lib.physad_xchg_export(self._h, buf), "xchg_export")
+        ok = self._lib.physad_xchg_export(self._h, buf) == 0
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(buf.raw), group=group)
-        blob = C.create_string_buffer(b"".join(handles), 64 * world)
-        check(self._lib.physad_xchg_connect(self._h, C.c_int(rank), C.c_int(world), blob), "xchg_connect")
-        dist.barrier(group)  # nobody launches an exchange before every rank has mapped every buffer
+        dist.all_gather_object(handles, bytes(buf.raw) if ok else None, group=group)
+        if ok and all(h is not None for h in handles):
+            blob = C.create_string_buffer(b"".join(handles), 64 * world)
+            ok = self._lib.physad_xchg_connect(self._h, C.c_int(rank), C.c_int(world), blob) == 0
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # also orders: nobody launches an exchange
+        if not bool(flag.item()):                                  # before every rank has mapped every buffer
+            self._lib.physad_xchg_disconnect(self._h)
+            self._peers = None
+            return False
         self._peers = (rank, world)
         return True
 
