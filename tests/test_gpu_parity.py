@@ -131,6 +131,39 @@ def test_generate_fields_bit_exact(ctx, checker, shape, H, per, m1p1):
         assert bits_equal(a, b) and np.all(np.isfinite(a))
 
 
+def test_error_paths_and_empty_inputs(ctx, checker):
+    """Status codes instead of crashes: bad arguments, unsupported shapes, missing weights, empty batches."""
+    import ctypes as C
+    import torch
+    from phys_autodiff_b200 import Grid, PhysadError, capi, ops
+    lib = capi.lib()
+    c2 = ops.Context()
+    try:
+        g = Grid(8, 8, 8, 1, 1, 1, 1e-3, True)
+        with pytest.raises(PhysadError, match="no weights"):
+            c2.mlp_grid_infer(g, 0.1)                                   # PHYSAD_E_NOWEIGHTS
+        w = checker.mlp_random_init(256, 1, 0.1)
+        c2.set_weights(_cfg(256), *w)
+        with pytest.raises(PhysadError, match="H > 128"):
+            c2.fused_loss_acc(g, 0.1, 1e-3)                             # PHYSAD_E_UNSUPPORTED
+        x = torch.zeros(0, 4, device="cuda")
+        assert c2.mlp_forward(x).shape == (0, 4)                         # empty batch is a no-op
+        w5 = [np.zeros(8 * 5, np.float32), np.zeros(8, np.float32), np.zeros(3 * 8, np.float32), np.zeros(3, np.float32)]
+        c2.set_weights(_cfg(8, True, 5, 3), *w5)
+        with pytest.raises(PhysadError, match="In = Out = 4"):
+            c2.mlp_grid_infer(g, 0.1)
+        c2.set_weights(_cfg(16), *checker.mlp_random_init(16, 1, 0.1))
+        for bad in (Grid(0, 8, 8), Grid(8, -1, 8), Grid(2048, 1024, 1024)):   # empty / negative / N >= 2^31
+            with pytest.raises(PhysadError):
+                c2.fused_loss_acc(bad, 0.1, 1e-3)
+        with pytest.raises(PhysadError, match="slab"):
+            c2.fused_loss_acc(g, 0.1, 1e-3, slab=(4, 12))
+        assert lib.physad_fused_loss_dev(c2._h, None, None, C.c_float(0), C.c_float(0), None, None, None, None, None, None) != 0
+        assert len(lib.physad_last_error()) > 0
+    finally:
+        c2.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # physics on supplied fields
 # ------------------------------------------------------------------------------------------------
