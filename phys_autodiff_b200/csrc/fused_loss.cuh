@@ -3,25 +3,30 @@
 //
 // Work decomposition
 //   work   = tiles x planes "tile-planes", linearised tile-major.  The grid is PERSISTENT: one block per
-//            resident slot (SMs x blocks/SM), block b owns the contiguous range [b W/G, (b+1) W/G) of
+//            resident slot (SMs x blocks/SM), block b owns the contiguous range [ranges[b], ranges[b+1]) of
 //            tile-planes, i.e. at most two z-segments of (usually) two different tiles -- every block
 //            gets the same COST (planes + the two time-t-only halo planes of every segment it starts;
 //            ranges are computed on the host, capi.cu: FusedPlan), so there is no partial last wave and
 //            no block that is slow because its range straddles two tiles.
 //   block  = marches along z over each of its segments of one (TX x TY) tile of (x,y) columns.
 //   thread = P columns that share x (rows ty, ty+TYB, ...); 32 lanes of a warp = 32 consecutive x.
-//   step k = plane zk = chunk_begin - 1 + k.  Interior steps evaluate all three time slices for
+//   step k = plane zk = segment_begin - 1 + k.  Interior steps evaluate all three time slices for
 //            the thread's columns (sharing the layer-1 prefix, see mlp_eval.cuh); the first and the
-//            last step are the chunk's z-halo and evaluate time t only.
+//            last step are the segment's z-halo and evaluate time t only.
 //   halo   = the stencil is the 7-point cross, so besides the tile only the ring of 2(TX+TY)
 //            columns around it is needed at time t.  Ring columns are recomputed from coordinates
 //            (the MLP is a pure function of (x,y,z,t): SURVEY.md section 8e) in 32-column tasks that
-//            rotate over the block's warps from plane to plane so no warp/SMSP is the slow one.
+//            rotate over the block's warps from plane to plane so no warp/SMSP is the slow one; the
+//            coordinate tables cxs/cys/czs (built on the host with the reference's float expressions)
+//            replace every per-point division.
 //   fields = time-t outputs of the last four planes live in shared memory ([4 planes][4 ch]
 //            [(TY+2) x (TX+2)]); the time differences (y(t+dt) - y(t-dt)) / (2 dt) of the plane whose
-//            residual is pending stay in registers.  One __syncthreads per plane.
+//            residual is pending stay in registers.  Planes are separated by a split-phase mbarrier
+//            (SPLITBAR: arrive after writing plane k, wait for plane k-1's barrier one plane later) or,
+//            in the cross-check variants, one __syncthreads per plane.
 //   residual (plane zk-1, formed at step k when plane zk is known): reference src/phys_cpu.cpp:66-109
-//            in fp32 (the reference's own CUDA kernels are fp32 too, src/phys_cuda_fused.cu:67-99);
+//            in fp32 (the reference's own CUDA kernels are fp32 too, src/phys_cuda_fused.cu:67-99) or, with
+//            DPRES, in double exactly as the CPU reference (bit-identical residuals);
 //            squares are accumulated per thread in double exactly like src/phys_cpu.cpp:140-145,
 //            then warp shuffle -> block -> per-block partial -> last block sums partials in index order
 //            (deterministic for a given launch geometry).
