@@ -470,6 +470,26 @@ def test_fused_full_size_128_properties(ctx, checker):
             assert abs(got[0] - s) <= 1e-6 * s
 
 
+def test_fused_large_anisotropic_grid_equals_staged_path(ctx, checker):
+    """A large non-cubic grid (23.6 M points, anisotropic spacing, clamp boundaries): the fused kernel's residuals
+    equal the staged GPU path (fields -> vectorised stencil kernel) bitwise and its loss equals the double sum
+    of its own residuals."""
+    import torch
+    og = OGrid(640, 384, 96, 0.5, 0.25, 2.0, 5e-3, False)
+    g = _g(og)
+    w = checker.mlp_random_init(32, 9, 0.3)
+    ctx.set_weights(_cfg(32), *w)
+    R = [torch.empty(og.N, device="cuda") for _ in range(4)]
+    acc = ctx.fused_loss_acc(g, 0.1, 5e-3, residuals=R).cpu().numpy()
+    f = ctx.mlp_generate_fields(g, 0.1, 5e-3)
+    acc2, R2 = ctx.phys_loss_acc(g, f, want_residuals=True)
+    for a, b in zip(R, R2):
+        assert torch.equal(a, b)
+    s0 = float(torch.sum(R[0].double() ** 2)); s1 = float(sum(torch.sum(r.double() ** 2) for r in R[1:]))
+    assert abs(acc[0] - s0) <= 1e-9 * s0 and abs(acc[1] - s1) <= 1e-9 * s1
+    assert np.allclose(acc2.cpu().numpy(), acc, rtol=1e-12)
+
+
 def test_fused_256_matches_own_residual_sum_and_slabs(ctx, checker):
     """BASELINE config 4 size (256^3, H=64): loss equals the double sum of the kernel's own residuals;
     8 slabs (the 8-GPU decomposition) sum to the same; residual planes spot-checked against the CPU."""
