@@ -120,6 +120,23 @@ int physad_mlp_generate_fields_dev(physad_ctx* ctx, const physad_grid* g, const 
 int physad_mlp_generate_fields_host(physad_ctx* ctx, const physad_grid* g, float t, float dt, float* sigma_tm1,
                                     float* sigma_t, float* sigma_tp1, float* u_tm1, float* u_t, float* u_tp1);
 
+/* ---- deeper MLPs (ADDITIVE: BASELINE config 5, depth sweep) ------------------------------------
+ * 4 -> H -> H -> ... -> H -> 4 with `hidden_layers` >= 1 hidden layers of width H (H = 32 or 64).  The
+ * reference API has exactly one hidden layer (include/mlp.h:5-6); further layers repeat its layer rule
+ * (src/mlp_cpu.cpp:19-24: from the bias, + W[g,h]*a[h] for h ascending, separate fp32 multiply and add,
+ * ReLU).  There is no reference implementation for hidden_layers > 1 (parity is against oracle/oracle.c's
+ * restatement only); hidden_layers == 1 is bit-identical to the one-hidden-layer entry points.
+ * Wh: (hidden_layers-1) matrices [H x H] row-major [g][h]; bh: (hidden_layers-1) x H.  HOST pointers.
+ * A later physad_set_weights() switches the context back to a one-hidden-layer network. */
+int physad_set_weights_deep(physad_ctx* ctx, const physad_mlp_config* cfg, int hidden_layers, const float* W1,
+                            const float* b1, const float* Wh, const float* bh, const float* W2, const float* b2);
+/* Stage-wise evaluation over the grid (coordinates from the index); outputs as the one-layer calls above. */
+int physad_mlp_grid_infer_deep_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float* out,
+                                   void* stream);
+int physad_mlp_generate_fields_deep_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float dt,
+                                        float* sigma_tm1, float* sigma_t, float* sigma_tp1, float* u_tm1, float* u_t,
+                                        float* u_tp1, void* stream);
+
 /* ---- physics operators on supplied fields (whole grid, single device) -------------------- */
 /* Residuals.  Replaces cuda_phys_residuals_fused / _nonfused (include/phys.h:67-77,120-130).
  * kernel_ms (host pointer, may be NULL) receives the kernel-only time of the _host variant, as the

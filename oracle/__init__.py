@@ -168,6 +168,23 @@ class PortOracle(_Oracle):
             out["R"] = tuple(R)
         return out
 
+    def mlp_forward_deep(self, x, L, W1, b1, Wh, bh, W2, b2, B, In, H, Out) -> np.ndarray:
+        """Deeper MLP (parity unpinned for L > 1, see oracle.c)."""
+        y = np.empty(B * Out, np.float32)
+        f = self.lib.oracle_mlp_forward_deep; f.restype = None
+        f(_fp(x), C.c_int(L), _fp(W1), _fp(b1), _fp(Wh if Wh is not None and Wh.size else None),
+          _fp(bh if bh is not None and bh.size else None), _fp(W2), _fp(b2), _fp(y), C.c_size_t(B), C.c_size_t(In),
+          C.c_size_t(H), C.c_size_t(Out))
+        return y
+
+    def mlp_grid_infer_deep(self, g: Grid, H, L, W1, b1, Wh, bh, W2, b2, t: float, m1p1: bool = True) -> np.ndarray:
+        out = np.empty(g.N * 4, np.float32)
+        f = self.lib.oracle_mlp_grid_infer_deep; f.restype = None
+        f(C.byref(g.c()), C.c_int(H), C.c_int(L), C.c_int(int(m1p1)), _fp(W1), _fp(b1),
+          _fp(Wh if Wh is not None and Wh.size else None), _fp(bh if bh is not None and bh.size else None), _fp(W2), _fp(b2),
+          C.c_float(t), _fp(out))
+        return out
+
     def sumsq(self, R, i0: int, i1: int):
         a_s, a_u = C.c_double(), C.c_double()
         f = self.lib.oracle_sumsq; f.restype = None

@@ -135,6 +135,56 @@ void oracle_mlp_forward(const float* x, const float* W1, const float* b1, const 
     free(a);
 }
 
+/* Deeper MLP: In -> H -> H -> ... -> H -> Out with L >= 1 hidden layers.  PARITY UNPINNED for L > 1: the reference
+ * has exactly one hidden layer (include/mlp.h:5-6), so there is nothing of the reference's to check this against.
+ * Every layer repeats the reference's layer rule (src/mlp_cpu.cpp:19-24,29-32): start from the bias, add
+ * W[g,h]*a[h] for h ascending with separately rounded fp32 multiply and add, ReLU on hidden layers.  For L == 1
+ * it must equal oracle_mlp_forward bit for bit (tests/test_oracle_cpu.py), which IS pinned to the reference.
+ * Wh: (L-1) matrices [H x H] row-major [g][h]; bh: (L-1) x H. */
+void oracle_mlp_forward_deep(const float* x, int L, const float* W1, const float* b1, const float* Wh, const float* bh,
+                             const float* W2, const float* b2, float* y, size_t B, size_t In, size_t H, size_t Out) {
+    float* a = (float*)malloc(sizeof(float) * (H ? H : 1));
+    float* a2 = (float*)malloc(sizeof(float) * (H ? H : 1));
+    for (size_t i = 0; i < B; ++i) {
+        const float* xi = x + i * In;
+        for (size_t h = 0; h < H; ++h) {
+            float s = b1[h];
+            for (size_t k = 0; k < In; ++k) s += W1[h * In + k] * xi[k];
+            a[h] = s > 0.f ? s : 0.f;
+        }
+        for (int l = 0; l + 1 < L; ++l) {
+            const float* W = Wh + (size_t)l * H * H;
+            const float* b = bh + (size_t)l * H;
+            for (size_t g = 0; g < H; ++g) {
+                float s = b[g];
+                for (size_t h = 0; h < H; ++h) s += W[g * H + h] * a[h];
+                a2[g] = s > 0.f ? s : 0.f;
+            }
+            float* t = a; a = a2; a2 = t;
+        }
+        for (size_t o = 0; o < Out; ++o) {
+            float s = b2[o];
+            for (size_t h = 0; h < H; ++h) s += W2[o * H + h] * a[h];
+            y[i * Out + o] = s;
+        }
+    }
+    free(a);
+    free(a2);
+}
+
+/* MLP over the grid at time t with a deep network (AoS out), coordinates as oracle_mlp_grid_infer. */
+void oracle_mlp_grid_infer_deep(const oracle_grid* g, int H, int L, int m1p1, const float* W1, const float* b1, const float* Wh,
+                                const float* bh, const float* W2, const float* b2, float t, float* out) {
+    const size_t N = (size_t)g->nx * g->ny * g->nz, chunk = 4096;
+    float* c = (float*)malloc(sizeof(float) * chunk * 4);
+    for (size_t p = 0; p < N; p += chunk) {
+        size_t n = N - p < chunk ? N - p : chunk;
+        coords_range(g, t, m1p1, p, n, c);
+        oracle_mlp_forward_deep(c, L, W1, b1, Wh, bh, W2, b2, out + p * 4, n, 4, (size_t)H, 4);
+    }
+    free(c);
+}
+
 /* MLP backward (MSE weight gradients), src/mlp_cpu.cpp:38-85: forward pass, gz2 = (2/float(B*Out))*(y - target),
  * then every gradient entry accumulated sequentially over the batch in fp32 (i ascending), gz1 =
  * (sum_o gz2[i,o]*W2[o,h]) * (z1 > 0). */

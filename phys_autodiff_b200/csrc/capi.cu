@@ -2,6 +2,7 @@
 // the host-pointer staging wrappers.  All arithmetic lives in the kernels (*.cuh); this file only
 // decides shapes, fills the kernel-parameter weight block and moves bytes.
 #include "../../include/physad_b200.h"
+#include "deep_mlp.cuh"
 #include "stage_kernels.cuh"
 
 #include <algorithm>
@@ -52,6 +53,10 @@ struct physad_ctx {
     uint64_t launches = 0;
     int fused_variant = 0;
     int exact_residuals = 0;  // 1: residual arithmetic in double exactly as the CPU reference; 0: fp32 with FMAs
+    // deeper MLPs (physad_set_weights_deep): hidden->hidden layers in the kernel's layout
+    int deep_layers = 0;          // L (0 = not set)
+    float *d_wh = nullptr, *d_bh = nullptr;
+    size_t d_wh_cap = 0, d_bh_cap = 0;
     // per-kernel launch facts on THIS device (opt-in shared memory set, resident blocks per SM): function
     // attributes are per device, so they are cached per context, not per process
     std::unordered_map<const void*, int> blocks_per_sm;
@@ -490,6 +495,41 @@ struct DeviceGuard {
 
 }  // namespace
 
+namespace {
+template <int H, bool FIELDS>
+int launch_deep(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], DeepArgs a, cudaStream_t st) {
+    const int nzl = s.z_end - s.z_begin;
+    if (nzl == 0) return 0;
+    if (nzl > 65535 || g->ny > 65535) return fail(PHYSAD_E_UNSUPPORTED, "deep MLP kernels: more than 65535 rows or planes per call");
+    if (int rc = ensure_coord_tables(c, g, st)) return rc;
+    a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.z_begin = s.z_begin; a.z_end = s.z_end;
+    a.hidden_layers = c->deep_layers;
+    a.cxs = c->tab.dev; a.cys = a.cxs + g->nx; a.czs = a.cys + g->ny;
+    a.wh = c->d_wh; a.bh = c->d_bh;
+    auto kern = k_mlp_deep<H, FIELDS>;
+    const size_t smem = size_t(H) * 128 * sizeof(float);
+    int& done = c->blocks_per_sm[reinterpret_cast<const void*>(kern)];
+    if (!done) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        done = 1;
+    }
+    MlpConst<H> k;
+    fill_const<H>(c, tc, k);
+    kern<<<dim3(unsigned((g->nx + 127) / 128), unsigned(g->ny), unsigned(nzl)), 128, smem, st>>>(k, a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int deep_ready(const physad_ctx* c, const char* what) {
+    if (!c->has_weights || c->deep_layers < 1) return fail(PHYSAD_E_NOWEIGHTS, std::string(what) + ": call physad_set_weights_deep first");
+    if (c->cfg.In != 4 || c->cfg.Out != 4 || (c->cfg.H != 32 && c->cfg.H != 64))
+        return fail(PHYSAD_E_UNSUPPORTED, std::string(what) + ": weights were replaced by a shape the deep kernels are not built for");
+    return 0;
+}
+}  // namespace
+
+
 // =================================================================================================
 extern "C" {
 
@@ -548,6 +588,7 @@ int physad_ctx_destroy(physad_ctx* c) {
     cudaFree(c->xbuf);
     cudaFree(c->plan.dev);
     cudaFree(c->tab.dev);
+    cudaFree(c->d_wh); cudaFree(c->d_bh);
     cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_acc); cudaFree(c->scratch);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -585,6 +626,7 @@ int physad_set_weights(physad_ctx* c, const physad_mlp_config* cfg, const float*
     // refreshed lazily there.
     c->dev_weights_stale = true;
     c->has_weights = true;
+    c->deep_layers = 0;  // a plain set_weights describes a one-hidden-layer network
     return 0;
 }
 
@@ -767,6 +809,81 @@ int physad_mlp_generate_fields_host(physad_ctx* c, const physad_grid* g, float t
         CU(cudaMemcpyAsync(dst[k], d + off[k], cnt[k] * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+// ---- deeper MLPs (additive; BASELINE config 5) ------------------------------------------------------
+int physad_set_weights_deep(physad_ctx* c, const physad_mlp_config* cfg, int hidden_layers, const float* W1, const float* b1,
+                            const float* Wh, const float* bh, const float* W2, const float* b2) {
+    if (!c || !cfg) return fail(PHYSAD_E_INVALID, "set_weights_deep: null argument");
+    if (cfg->In != 4 || cfg->Out != 4 || (cfg->H != 32 && cfg->H != 64))
+        return fail(PHYSAD_E_UNSUPPORTED, "set_weights_deep: In = Out = 4 and H in {32, 64} are built");
+    if (hidden_layers < 1 || hidden_layers > 16) return fail(PHYSAD_E_INVALID, "set_weights_deep: 1 <= hidden_layers <= 16");
+    if (hidden_layers > 1 && (!Wh || !bh)) return fail(PHYSAD_E_INVALID, "set_weights_deep: null hidden weights");
+    if (int rc = physad_set_weights(c, cfg, W1, b1, W2, b2)) return rc;
+    DeviceGuard dg(c->device);
+    const size_t H = size_t(cfg->H), nl = size_t(hidden_layers - 1);
+    std::vector<float> wt(std::max<size_t>(1, nl * H * H));
+    for (size_t l = 0; l < nl; ++l)          // [g][h] row-major -> [h][g] with output pairs stored (g+1, g)
+        for (size_t h = 0; h < H; ++h)
+            for (size_t g = 0; g < H; g += 2) {
+                wt[(l * H + h) * H + g] = Wh[(l * H + g + 1) * H + h];
+                wt[(l * H + h) * H + g + 1] = Wh[(l * H + g) * H + h];
+            }
+    if (wt.size() > c->d_wh_cap) {
+        if (c->d_wh) CU(cudaFree(c->d_wh));
+        c->d_wh = nullptr; c->d_wh_cap = 0;
+        CU(cudaMalloc(&c->d_wh, wt.size() * sizeof(float)));
+        c->d_wh_cap = wt.size();
+    }
+    const size_t nb = std::max<size_t>(1, nl * H);
+    if (nb > c->d_bh_cap) {
+        if (c->d_bh) CU(cudaFree(c->d_bh));
+        c->d_bh = nullptr; c->d_bh_cap = 0;
+        CU(cudaMalloc(&c->d_bh, nb * sizeof(float)));
+        c->d_bh_cap = nb;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (nl) {
+        CU(cudaMemcpy(c->d_wh, wt.data(), nl * H * H * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_bh, bh, nl * H * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    c->deep_layers = hidden_layers;
+    return 0;
+}
+
+int physad_mlp_grid_infer_deep_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, float t, float* out,
+                                   void* stream) {
+    if (!c || !out) return fail(PHYSAD_E_INVALID, "mlp_grid_infer_deep: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = deep_ready(c, "mlp_grid_infer_deep")) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    if (uintptr_t(out) % 16) return fail(PHYSAD_E_INVALID, "mlp_grid_infer_deep: out must be 16-byte aligned");
+    DeviceGuard dg(c->device);
+    const float tcv = time_coord(t, c->cfg.norm);
+    const float tc[3] = {tcv, tcv, tcv};
+    DeepArgs a{};
+    a.out_aos = reinterpret_cast<float4*>(out);
+    return c->cfg.H == 32 ? launch_deep<32, false>(c, g, s, tc, a, cudaStream_t(stream))
+                          : launch_deep<64, false>(c, g, s, tc, a, cudaStream_t(stream));
+}
+
+int physad_mlp_generate_fields_deep_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, float t, float dt,
+                                        float* s_m, float* s_0, float* s_p, float* u_m, float* u_0, float* u_p,
+                                        void* stream) {
+    if (!c || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p) return fail(PHYSAD_E_INVALID, "generate_fields_deep: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = deep_ready(c, "generate_fields_deep")) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    DeviceGuard dg(c->device);
+    const float ts[3] = {t - dt, t, t + dt};
+    const float tc[3] = {time_coord(ts[0], c->cfg.norm), time_coord(ts[1], c->cfg.norm), time_coord(ts[2], c->cfg.norm)};
+    DeepArgs a{};
+    a.sigma[0] = s_m; a.sigma[1] = s_0; a.sigma[2] = s_p;
+    a.u[0] = u_m; a.u[1] = u_0; a.u[2] = u_p;
+    return c->cfg.H == 32 ? launch_deep<32, true>(c, g, s, tc, a, cudaStream_t(stream))
+                          : launch_deep<64, true>(c, g, s, tc, a, cudaStream_t(stream));
 }
 
 // ---- physics on supplied fields ------------------------------------------------------------------

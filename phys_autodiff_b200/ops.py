@@ -149,6 +149,36 @@ class Context:
                                                        self._stream()), "mlp_generate_fields")
         return s[0], s[1], s[2], u[0], u[1], u[2]
 
+    # -- deeper MLPs (additive, BASELINE config 5) -----------------------------------------------------
+    def set_weights_deep(self, cfg: MLPConfig, hidden_layers: int, W1, b1, Wh, bh, W2, b2) -> None:
+        """L = hidden_layers >= 1 hidden layers of width H; Wh: (L-1) x [H x H] row-major, bh: (L-1) x H."""
+        W1, b1, W2, b2 = _f32(W1), _f32(b1), _f32(W2), _f32(b2)
+        Wh = _f32(Wh if Wh is not None else np.zeros(0)); bh = _f32(bh if bh is not None else np.zeros(0))
+        assert Wh.size == (hidden_layers - 1) * cfg.H * cfg.H and bh.size == (hidden_layers - 1) * cfg.H
+        c = cfg.c()
+        check(self._lib.physad_set_weights_deep(self._h, C.byref(c), C.c_int(hidden_layers), ptr(W1), ptr(b1),
+                                                ptr(Wh) if Wh.size else None, ptr(bh) if bh.size else None, ptr(W2), ptr(b2)),
+              "set_weights_deep")
+        self.cfg = cfg
+
+    def mlp_grid_infer_deep(self, g: Grid, t: float, slab=None):
+        cs, n = self._slab(g, slab)
+        out = self._empty(n * 4)
+        cg = g.c()
+        check(self._lib.physad_mlp_grid_infer_deep_dev(self._h, C.byref(cg), C.byref(cs), C.c_float(t), ptr(out),
+                                                       self._stream()), "mlp_grid_infer_deep")
+        return out.view(n, 4)
+
+    def mlp_generate_fields_deep(self, g: Grid, t: float, dt: float, slab=None):
+        cs, n = self._slab(g, slab)
+        s = [self._empty(n) for _ in range(3)]
+        u = [self._empty(3 * n) for _ in range(3)]
+        cg = g.c()
+        check(self._lib.physad_mlp_generate_fields_deep_dev(self._h, C.byref(cg), C.byref(cs), C.c_float(t), C.c_float(dt),
+                                                            ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(u[0]), ptr(u[1]), ptr(u[2]),
+                                                            self._stream()), "mlp_generate_fields_deep")
+        return s[0], s[1], s[2], u[0], u[1], u[2]
+
     # -- physics on supplied device fields -----------------------------------------------------------
     def phys_residuals(self, g: Grid, fields: Sequence):
         R = [self._empty(g.N) for _ in range(4)]

@@ -131,6 +131,34 @@ def test_generate_fields_bit_exact(ctx, checker, shape, H, per, m1p1):
         assert bits_equal(a, b) and np.all(np.isfinite(a))
 
 
+@pytest.mark.parametrize("H,L", [(64, 1), (64, 2), (64, 4), (32, 1), (32, 3), (32, 6)])
+def test_deep_mlp_bit_exact(ctx, port, checker, H, L):
+    """Deeper MLPs (additive API, BASELINE config 5): GPU == CPU restatement bitwise for every depth; with one
+    hidden layer the deep entry points equal the reference-pinned one-layer path."""
+    rng = np.random.default_rng(100 * H + L)
+    og = OGrid(70, 9, 5, 1, 1, 1, 2e-3, True)
+    g = _g(og)
+    W1, b1, W2, b2 = checker.mlp_random_init(H, 777, 0.25)
+    Wh = rng.uniform(-0.2, 0.2, (L - 1) * H * H).astype(np.float32)
+    bh = rng.uniform(-0.2, 0.2, (L - 1) * H).astype(np.float32)
+    ctx.set_weights_deep(_cfg(H), L, W1, b1, Wh, bh, W2, b2)
+    got = ctx.mlp_grid_infer_deep(g, 0.3).cpu().numpy().reshape(-1)
+    want = port.mlp_grid_infer_deep(og, H, L, W1, b1, Wh, bh, W2, b2, 0.3)
+    assert bits_equal(got, want)
+    f = ctx.mlp_generate_fields_deep(g, 0.25, 2e-3)
+    for k, tt in enumerate((np.float32(0.25) - np.float32(2e-3), np.float32(0.25), np.float32(0.25) + np.float32(2e-3))):
+        y = port.mlp_grid_infer_deep(og, H, L, W1, b1, Wh, bh, W2, b2, float(tt)).reshape(-1, 4)
+        assert bits_equal(f[k].cpu().numpy(), y[:, 0])
+        assert bits_equal(f[3 + k].cpu().numpy(), np.concatenate([y[:, 1], y[:, 2], y[:, 3]]))
+    if L == 1:
+        ctx.set_weights(_cfg(H), W1, b1, W2, b2)
+        assert bits_equal(ctx.mlp_grid_infer(g, 0.3).cpu().numpy().reshape(-1), got)
+        assert bits_equal(checker.mlp_grid_infer(og, (W1, b1, W2, b2), 0.3), got)   # pinned to the reference
+    # the physics operators take the deep fields like any others
+    ls, lu = ctx.phys_loss(g, _pw(), f)
+    assert np.isfinite(ls) and np.isfinite(lu)
+
+
 def test_error_paths_and_empty_inputs(ctx, checker):
     """Status codes instead of crashes: bad arguments, unsupported shapes, missing weights, empty batches."""
     import ctypes as C

@@ -60,6 +60,21 @@ def test_mlp_backward_matches_golden(port, golden):
         assert bits_equal(a, arr["bwd_" + k]), k
 
 
+def test_deep_oracle_with_one_hidden_layer_is_the_pinned_forward(port):
+    """oracle_mlp_forward_deep is unpinned for L > 1; its L = 1 case must equal the reference-pinned forward."""
+    rng = np.random.default_rng(5)
+    B, In, H, Out = 200, 4, 64, 4
+    x = rng.uniform(-1, 1, B * In).astype(np.float32)
+    W1 = rng.uniform(-.4, .4, H * In).astype(np.float32); b1 = rng.uniform(-.4, .4, H).astype(np.float32)
+    W2 = rng.uniform(-.4, .4, Out * H).astype(np.float32); b2 = rng.uniform(-.4, .4, Out).astype(np.float32)
+    assert bits_equal(port.mlp_forward_deep(x, 1, W1, b1, None, None, W2, b2, B, In, H, Out),
+                      port.mlp_forward(x, W1, b1, W2, b2, B, In, H, Out))
+    # L = 2 with an identity-like middle layer (W = I, b = 0) reproduces L = 1: relu(a) = a for a >= 0
+    Wh = np.eye(H, dtype=np.float32).reshape(-1); bh = np.zeros(H, np.float32)
+    assert bits_equal(port.mlp_forward_deep(x, 2, W1, b1, Wh, bh, W2, b2, B, In, H, Out),
+                      port.mlp_forward(x, W1, b1, W2, b2, B, In, H, Out))
+
+
 def test_anchor_losses_64cubed(port, golden):
     """Scalar anchors at a BASELINE size (also listed in SURVEY.md section 7 / BASELINE.md section 2)."""
     _, meta = golden
