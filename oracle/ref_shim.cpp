@@ -149,9 +149,8 @@ int ref_fused_loss_mt(const CGrid* g, int In, int H, int Out, int norm_m1p1, con
     std::vector<float> sig[3], u[3];
     for (int s = 0; s < 3; ++s) { sig[s].resize(N); u[s].resize(3 * N); }
 
-    // z-plane ranges per worker; coordinates for a plane range come from the reference's own
-    // make_grid_coords on the full-(nx,ny) sub-grid?  No: z normalisation uses the global nz, so the
-    // coordinate array is generated once per time slice with the reference function and then sliced.
+    // The coordinate array of a time slice is generated once with the reference's own make_grid_coords (the z
+    // normalisation uses the global nz) and the workers take disjoint chunks of points from it.
     for (int s = 0; s < 3; ++s) {
         std::vector<float> coords;
         phys::make_grid_coords(spec, ts[s], cfg.norm, coords);
