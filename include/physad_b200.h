@@ -243,6 +243,21 @@ void physad_finalize_loss(const double acc[2], const physad_phys_weights* w, siz
 void physad_mlp_random_init(int In, int H, int Out, unsigned int seed, float scale, float* W1, float* b1, float* W2,
                             float* b2);
 
+/* ---- closed loop (ADDITIVE: the reference plans it, REQUIREMENT.md:155-169, but stops at dL/dR,
+ * src/phys_cpu.cpp:151-170, and its MLP backward is the MSE one, src/mlp_cpu.cpp:38-85) ----------------
+ * Loss of the MLP-generated fields AND the gradient of L_sigma + L_u (weights w included, mean over N) with
+ * respect to the MLP weights set by physad_set_weights: forward stage-wise on the device (fields of the three
+ * slices and residuals kept in a context-owned workspace of 64 B/point), then one backward kernel that
+ * transposes the stencil and back-propagates through the MLP.  acc: 2 device doubles (sum R_sigma^2, sum |R_u|^2,
+ * see physad_finalize_loss); grad: 9H+4 device doubles laid out  dW1[H*4] | db1[H] | dW2[4*H] | db2[4]  (the
+ * reference's W1/b1/W2/b2 layouts).  Whole grid on one GPU.  The host form takes/returns host buffers (any
+ * gradient pointer may be null) and replaces the weights first when cfg != NULL. */
+int physad_fused_loss_grad_dev(physad_ctx* ctx, const physad_grid* g, const physad_phys_weights* w, float t, float dt,
+                               double* acc, double* grad, void* stream);
+int physad_fused_loss_grad_host(physad_ctx* ctx, const physad_grid* g, const physad_mlp_config* cfg, const float* W1,
+                                const float* b1, const float* W2, const float* b2, const physad_phys_weights* w, float t,
+                                float dt, float* loss_sigma, float* loss_u, float* dW1, float* db1, float* dW2, float* db2);
+
 /* Host-only: the work partition the fused kernel is launched with.  The sequence of tiles x planes
  * tile-planes (tile-major) is cut into at most `slots` contiguous ranges of equal cost, a range paying
  * ~0.9 plane-equivalents for every z-segment it starts (its recomputed halo planes).  Writes the

@@ -185,6 +185,30 @@ class PortOracle(_Oracle):
           C.c_float(t), _fp(out))
         return out
 
+    def phys_loss_grad(self, g: Grid, w, t, dt, w_sigma=1.0, w_u=1.0, m1p1=True, all_double=False):
+        """d(L_sigma + L_u)/d(weights) (oracle_grad.c; parity unpinned) -> dict(loss_sigma, loss_u, grad[9H+4] f64)."""
+        W1, b1, W2, b2 = w
+        H = b1.size
+        ls, lu = C.c_double(), C.c_double()
+        grad = np.empty(9 * H + 4, np.float64)
+        f = self.lib.oracle_phys_loss_grad; f.restype = C.c_int
+        rc = f(C.byref(g.c()), C.c_int(H), C.c_int(int(m1p1)), _fp(W1), _fp(b1), _fp(W2), _fp(b2), C.c_float(t),
+               C.c_float(dt), C.c_float(w_sigma), C.c_float(w_u), C.c_int(int(all_double)), C.byref(ls), C.byref(lu),
+               grad.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0
+        return dict(loss_sigma=ls.value, loss_u=lu.value, grad=grad)
+
+    def phys_loss_double(self, g: Grid, theta: np.ndarray, H: int, t, dt, w_sigma=1.0, w_u=1.0, m1p1=True):
+        """All-double L_sigma, L_u of double weights theta[9H+4] (the function finite differences probe)."""
+        theta = np.ascontiguousarray(theta, np.float64)
+        assert theta.size == 9 * H + 4
+        ls, lu = C.c_double(), C.c_double()
+        f = self.lib.oracle_phys_loss_double; f.restype = C.c_int
+        rc = f(C.byref(g.c()), C.c_int(H), C.c_int(int(m1p1)), theta.ctypes.data_as(C.POINTER(C.c_double)), C.c_float(t),
+               C.c_float(dt), C.c_float(w_sigma), C.c_float(w_u), C.byref(ls), C.byref(lu))
+        assert rc == 0
+        return ls.value, lu.value
+
     def sumsq(self, R, i0: int, i1: int):
         a_s, a_u = C.c_double(), C.c_double()
         f = self.lib.oracle_sumsq; f.restype = None
@@ -224,7 +248,8 @@ def port() -> PortOracle:
     global _PORT
     if _PORT is None:
         path = os.path.join(_HERE, "_build", "liboracle.so")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "oracle.c")):
+        if not os.path.exists(path) or os.path.getmtime(path) < max(
+                os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "oracle_grad.c")):
             build(ref_too=False)
         _PORT = PortOracle(C.CDLL(path), "oracle_")
     return _PORT

@@ -3,6 +3,7 @@
 // decides shapes, fills the kernel-parameter weight block and moves bytes.
 #include "../../include/physad_b200.h"
 #include "deep_mlp.cuh"
+#include "grad_kernels.cuh"
 #include "stage_kernels.cuh"
 
 #include <algorithm>
@@ -50,6 +51,13 @@ struct physad_ctx {
     double* h_acc = nullptr;  // pinned [2]
     char* scratch = nullptr;  // device staging for *_host calls
     size_t scratch_cap = 0;
+    // closed-loop gradient (physad_fused_loss_grad_*): fields + residuals workspace, block partials, result
+    float* gws = nullptr;
+    size_t gws_cap = 0;
+    double* gpart = nullptr;
+    size_t gpart_cap = 0;
+    double* d_grad = nullptr;   // [9 * 128 + 4]
+    double* h_grad = nullptr;   // pinned, same size
     uint64_t launches = 0;
     int fused_variant = 0;
     int exact_residuals = 0;  // 1: residual arithmetic in double exactly as the CPU reference; 0: fp32 with FMAs
@@ -496,6 +504,32 @@ struct DeviceGuard {
 }  // namespace
 
 namespace {
+template <int HT>
+int launch_grad_t(physad_ctx* c, const GradArgs& a, size_t chunks, cudaStream_t st) {
+    auto kern = k_phys_grad<HT>;
+    int& bps = c->blocks_per_sm[reinterpret_cast<const void*>(kern)];
+    if (!bps) {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, GRAD_THREADS, 0));
+        if (bps < 1) return fail(PHYSAD_E_UNSUPPORTED, "fused_loss_grad: kernel does not fit an SM");
+    }
+    const size_t blocks = std::max<size_t>(1, std::min<size_t>(chunks, size_t(c->sm_count) * bps));
+    const size_t need = blocks * (9 * HT + 4);
+    if (need > c->gpart_cap) {
+        if (c->gpart) CU(cudaFree(c->gpart));
+        c->gpart = nullptr; c->gpart_cap = 0;
+        CU(cudaMalloc(&c->gpart, need * sizeof(double)));
+        c->gpart_cap = need;
+    }
+    GradArgs k = a;
+    k.partials = c->gpart;
+    kern<<<unsigned(blocks), GRAD_THREADS, 0, st>>>(k);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+namespace {
 template <int H, bool FIELDS>
 int launch_deep(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], DeepArgs a, cudaStream_t st) {
     const int nzl = s.z_end - s.z_begin;
@@ -590,6 +624,8 @@ int physad_ctx_destroy(physad_ctx* c) {
     cudaFree(c->tab.dev);
     cudaFree(c->d_wh); cudaFree(c->d_bh);
     cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_acc); cudaFree(c->scratch);
+    cudaFree(c->gws); cudaFree(c->gpart); cudaFree(c->d_grad);
+    if (c->h_grad) cudaFreeHost(c->h_grad);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1110,6 +1146,82 @@ int physad_fused_loss_allreduce_dev(physad_ctx* c, const physad_grid* g, const p
     DeviceGuard dg(c->device);
     float* R[4] = {Rs, Rx, Ry, Rz};
     return launch_fused(c, g, s, t, dt, acc, R, cudaStream_t(stream), true);
+}
+
+// ---- closed loop: loss and its gradient with respect to the MLP weights (additive, grad_kernels.cuh) ----
+
+int physad_fused_loss_grad_dev(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w, float t, float dt,
+                               double* acc, double* grad, void* stream) {
+    if (!c || !w || !acc || !grad) return fail(PHYSAD_E_INVALID, "fused_loss_grad: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = need_4x4(c, "fused_loss_grad")) return rc;
+    DeviceGuard dg(c->device);
+    cudaStream_t st = cudaStream_t(stream);
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    if (16 * N > c->gws_cap) {
+        if (c->gws) CU(cudaFree(c->gws));
+        c->gws = nullptr; c->gws_cap = 0;
+        CU(cudaMalloc(&c->gws, 16 * N * sizeof(float)));
+        c->gws_cap = 16 * N;
+    }
+    // forward, stage-wise on the device: fields of the three slices, then residuals + the two sums
+    float* f = c->gws;
+    float *s_m = f, *s_0 = f + N, *s_p = f + 2 * N, *u_m = f + 3 * N, *u_0 = f + 6 * N, *u_p = f + 9 * N, *R = f + 12 * N;
+    if (int rc = physad_mlp_generate_fields_dev(c, g, nullptr, t, dt, s_m, s_0, s_p, u_m, u_0, u_p, stream)) return rc;
+    if (int rc = physad_phys_loss_dev(c, g, s_m, s_0, s_p, u_m, u_0, u_p, acc, R, R + N, R + 2 * N, R + 3 * N, stream)) return rc;
+    // backward
+    if (int rc = upload_weights_if_stale(c, st)) return rc;
+    if (int rc = ensure_coord_tables(c, g, st)) return rc;
+    GradArgs a{};
+    a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
+    a.z_begin = 0; a.z_end = g->nz; a.z_origin = 0;
+    a.periodic = g->periodic != 0; a.wrap_z = a.periodic;
+    a.cstride = N;
+    a.s0 = s_0; a.u0 = u_0;
+    for (int k = 0; k < 4; ++k) a.R[k] = R + k * N;
+    a.cxs = c->tab.dev; a.cys = a.cxs + g->nx; a.czs = a.cys + g->ny;
+    vjp_scales(g, w, &a.scale_s, &a.scale_u);
+    a.inv2dt = inv2(dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
+    const float ts[3] = {t - dt, t, t + dt};
+    for (int k = 0; k < 3; ++k) a.tc[k] = time_coord(ts[k], c->cfg.norm);
+    a.W1 = c->dW1; a.b1 = c->db1; a.W2 = c->dW2;
+    a.H = c->cfg.H;
+    a.ticket = c->ticket;
+    a.grad = grad;
+    const size_t chunks = (N + GRAD_THREADS - 1) / GRAD_THREADS;
+    switch (template_h(c->cfg.H)) {
+        case 32: return launch_grad_t<32>(c, a, chunks, st);
+        case 64: return launch_grad_t<64>(c, a, chunks, st);
+        case 128: return launch_grad_t<128>(c, a, chunks, st);
+    }
+    return fail(PHYSAD_E_UNSUPPORTED, "H > 128 not built");
+}
+
+int physad_fused_loss_grad_host(physad_ctx* c, const physad_grid* g, const physad_mlp_config* cfg, const float* W1,
+                                const float* b1, const float* W2, const float* b2, const physad_phys_weights* w, float t,
+                                float dt, float* loss_sigma, float* loss_u, float* dW1, float* db1, float* dW2, float* db2) {
+    if (!c || !w) return fail(PHYSAD_E_INVALID, "fused_loss_grad: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (cfg) {
+        if (int rc = physad_set_weights(c, cfg, W1, b1, W2, b2)) return rc;
+    }
+    if (int rc = need_4x4(c, "fused_loss_grad")) return rc;
+    DeviceGuard dg(c->device);
+    constexpr size_t cap = 9 * 128 + 4;
+    if (!c->d_grad) CU(cudaMalloc(&c->d_grad, cap * sizeof(double)));
+    if (!c->h_grad) CU(cudaMallocHost(&c->h_grad, cap * sizeof(double)));
+    if (int rc = physad_fused_loss_grad_dev(c, g, w, t, dt, c->d_acc, c->d_grad, c->stream)) return rc;
+    const int H = c->cfg.H;
+    CU(cudaMemcpyAsync(c->h_acc, c->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_grad, c->d_grad, size_t(9 * H + 4) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    physad_finalize_loss(c->h_acc, w, size_t(g->nx) * g->ny * g->nz, loss_sigma, loss_u);
+    const double* gd = c->h_grad;
+    if (dW1) for (int i = 0; i < 4 * H; ++i) dW1[i] = float(gd[i]);
+    if (db1) for (int i = 0; i < H; ++i) db1[i] = float(gd[4 * H + i]);
+    if (dW2) for (int i = 0; i < 4 * H; ++i) dW2[i] = float(gd[5 * H + i]);
+    if (db2) for (int i = 0; i < 4; ++i) db2[i] = float(gd[9 * H + i]);
+    return 0;
 }
 
 int physad_plan_ranges(int tiles, int planes, int slots, int* out, int out_cap) {

@@ -355,6 +355,36 @@ class Context:
         ls, lu = self.finalize(self._read_acc(acc), pw, g.N)
         return (ls, lu, tuple(R)) if want_residuals else (ls, lu)
 
+    # -- closed loop: loss + gradient with respect to the MLP weights (additive) ----------------------------
+    def fused_loss_grad_acc(self, g: Grid, pw: PhysWeights, t: float, dt: float, acc=None, grad=None):
+        """Device form: returns (acc[2], grad[9H+4]) float64 device tensors; grad = dW1 | db1 | dW2 | db2."""
+        import torch
+        acc = acc if acc is not None else self._empty(2, torch.float64)
+        grad = grad if grad is not None else self._empty(9 * self.cfg.H + 4, torch.float64)
+        cg, cw = g.c(), pw.c()
+        check(self._lib.physad_fused_loss_grad_dev(self._h, C.byref(cg), C.byref(cw), C.c_float(t), C.c_float(dt),
+                                                   ptr(acc), ptr(grad), self._stream()), "fused_loss_grad")
+        return acc, grad
+
+    def fused_loss_grad(self, g: Grid, pw: PhysWeights, t: float, dt: float):
+        """(L_sigma, L_u, grad float64 ndarray[9H+4]) of the weights set by set_weights()."""
+        acc, grad = self.fused_loss_grad_acc(g, pw, t, dt)
+        gh = grad.cpu().numpy()
+        ls, lu = self.finalize(self._read_acc(acc), pw, g.N)
+        return ls, lu, gh
+
+    def fused_loss_grad_host(self, g: Grid, cfg: MLPConfig, W1, b1, W2, b2, pw: PhysWeights, t: float, dt: float):
+        """Host-buffer form: weights in, (L_sigma, L_u, dW1, db1, dW2, db2) out (float32, the reference's layouts)."""
+        W1, b1, W2, b2 = _f32(W1), _f32(b1), _f32(W2), _f32(b2)
+        d = [np.empty(4 * cfg.H, np.float32), np.empty(cfg.H, np.float32), np.empty(4 * cfg.H, np.float32), np.empty(4, np.float32)]
+        ls, lu = C.c_float(), C.c_float()
+        cg, cc, cw = g.c(), cfg.c(), pw.c()
+        check(self._lib.physad_fused_loss_grad_host(self._h, C.byref(cg), C.byref(cc), ptr(W1), ptr(b1), ptr(W2), ptr(b2),
+                                                    C.byref(cw), C.c_float(t), C.c_float(dt), C.byref(ls), C.byref(lu),
+                                                    *[ptr(x) for x in d]), "fused_loss_grad_host")
+        self.cfg = cfg
+        return (np.float32(ls.value), np.float32(lu.value), *d)
+
     # -- host-buffer forms (the reference's contract) -----------------------------------------------------
     def fused_loss_host(self, g: Grid, cfg: MLPConfig, W1, b1, W2, b2, pw: PhysWeights, t: float, dt: float,
                         want_residuals: bool = False):
@@ -524,3 +554,8 @@ def cuda_phys_loss_backward_fused(g: Grid, pw: PhysWeights, fields):
 
 def mlp_phys_loss_fused_cuda(g: Grid, cfg: MLPConfig, w, pw: PhysWeights, t: float, dt: float, want_residuals: bool = False):
     return default_context().fused_loss_host(g, cfg, *w, pw, t, dt, want_residuals)
+
+
+def mlp_phys_loss_grad_cuda(g: Grid, cfg: MLPConfig, w, pw: PhysWeights, t: float, dt: float):
+    """Closed loop (additive): losses and d(L_sigma + L_u)/d(W1, b1, W2, b2)."""
+    return default_context().fused_loss_grad_host(g, cfg, *w, pw, t, dt)
