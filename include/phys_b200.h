@@ -24,6 +24,13 @@ void mlp_phys_loss_fused_cuda(const GridSpec& g, const MLPGridConfig& cfg, const
                               float t, float dt, float* out_loss_sigma, float* out_loss_u, float* opt_R_sigma = nullptr,
                               float* opt_R_ux = nullptr, float* opt_R_uy = nullptr, float* opt_R_uz = nullptr);
 
+// The closed loop the reference plans in REQUIREMENT.md:155-169 ("MLP backward: pass dL/dsigma, dL/du to the MLP
+// weights") and stops short of (cpu_phys_loss_backward returns dL/dR only): the two losses of the MLP-generated
+// fields AND d(L_sigma + L_u)/d(weights), the loss VJP carried through the transposed stencil and the MLP on the
+// device.  `grad` is resized to the shapes of `w` (W1 [H x In], b1, W2 [Out x H], b2).  Same requirements as above.
+void mlp_phys_loss_grad_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, const PhysWeights& pw,
+                             float t, float dt, float* out_loss_sigma, float* out_loss_u, MLPWeights& grad);
+
 }  // namespace phys
 
 #endif  // PHYS_AUTODIFF_PHYS_B200_H

@@ -58,6 +58,7 @@ struct physad_ctx {
     size_t gpart_cap = 0;
     double* d_grad = nullptr;   // [9 * 128 + 4]
     double* h_grad = nullptr;   // pinned, same size
+    int grad_blocks_per_sm[3] = {0, 0, 0};   // HT = 32, 64, 128 on this device
     uint64_t launches = 0;
     int fused_variant = 0;
     int exact_residuals = 0;  // 1: residual arithmetic in double exactly as the CPU reference; 0: fp32 with FMAs
@@ -504,16 +505,14 @@ struct DeviceGuard {
 }  // namespace
 
 namespace {
-template <int HT>
-int launch_grad_t(physad_ctx* c, const GradArgs& a, size_t chunks, cudaStream_t st) {
-    auto kern = k_phys_grad<HT>;
-    int& bps = c->blocks_per_sm[reinterpret_cast<const void*>(kern)];
+int launch_grad(physad_ctx* c, int HT, const GradArgs& a, size_t chunks, cudaStream_t st) {
+    int& bps = c->grad_blocks_per_sm[HT == 32 ? 0 : (HT == 64 ? 1 : 2)];
     if (!bps) {
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, GRAD_THREADS, 0));
+        CU(cudaError_t(grad_blocks_per_sm(HT, &bps)));
         if (bps < 1) return fail(PHYSAD_E_UNSUPPORTED, "fused_loss_grad: kernel does not fit an SM");
     }
     const size_t blocks = std::max<size_t>(1, std::min<size_t>(chunks, size_t(c->sm_count) * bps));
-    const size_t need = blocks * (9 * HT + 4);
+    const size_t need = blocks * (GRAD_NACC * HT + 4);
     if (need > c->gpart_cap) {
         if (c->gpart) CU(cudaFree(c->gpart));
         c->gpart = nullptr; c->gpart_cap = 0;
@@ -522,9 +521,8 @@ int launch_grad_t(physad_ctx* c, const GradArgs& a, size_t chunks, cudaStream_t 
     }
     GradArgs k = a;
     k.partials = c->gpart;
-    kern<<<unsigned(blocks), GRAD_THREADS, 0, st>>>(k);
     c->launches++;
-    CU(cudaGetLastError());
+    CU(cudaError_t(grad_launch(HT, k, unsigned(blocks), st)));
     return 0;
 }
 }  // namespace
@@ -1189,12 +1187,7 @@ int physad_fused_loss_grad_dev(physad_ctx* c, const physad_grid* g, const physad
     a.ticket = c->ticket;
     a.grad = grad;
     const size_t chunks = (N + GRAD_THREADS - 1) / GRAD_THREADS;
-    switch (template_h(c->cfg.H)) {
-        case 32: return launch_grad_t<32>(c, a, chunks, st);
-        case 64: return launch_grad_t<64>(c, a, chunks, st);
-        case 128: return launch_grad_t<128>(c, a, chunks, st);
-    }
-    return fail(PHYSAD_E_UNSUPPORTED, "H > 128 not built");
+    return launch_grad(c, template_h(c->cfg.H), a, chunks, st);
 }
 
 int physad_fused_loss_grad_host(physad_ctx* c, const physad_grid* g, const physad_mlp_config* cfg, const float* W1,

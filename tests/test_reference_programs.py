@@ -53,3 +53,11 @@ def test_reference_mlp_compare_reports_zero_difference():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     diffs = [float(v) for v in re.findall(r"(?:diff|err)[^=:\n]*[=:]\s*([0-9.eE+-]+)", r.stdout)]
     assert diffs and all(d == 0.0 for d in diffs), r.stdout[-2000:]
+
+
+def test_closed_loop_program_through_the_cxx_api():
+    """tests/refprogs/closed_loop_train.cpp (ours, in the reference's style): Adam over phys::mlp_phys_loss_grad_cuda;
+    the plan's acceptance criterion (REQUIREMENT.md:164-169): L falls >= 90 % within K steps."""
+    r = _run("closed_loop_train")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "[PASS]" in r.stdout
