@@ -388,6 +388,22 @@ def main():
             extra[f"H{H2}"] = {"value": g.N * 10 / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / 10,
                                "roofline_frac": flops_per_point(H2) * g.N * 10 / (t_ms * 1e-3) / 1e12 / peak_strict}
         ctx.set_weights(cfg, *w)
+        # the closed loop (additive): losses + d(L_sigma + L_u)/d(weights) per step, device-resident
+        pwc = PhysWeights(1.0, 1.0)
+        gacc, ggrad = ctx.fused_loss_grad_acc(g, pwc, T0, DT)
+        for _ in range(3):
+            ctx.fused_loss_grad_acc(g, pwc, T0, DT, gacc, ggrad)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record()
+            ctx.fused_loss_grad_acc(g, pwc, T0, DT, gacc, ggrad)
+            e1.record()
+        torch.cuda.synchronize()
+        gms = sorted(e0.elapsed_time(e1) for e0, e1 in evs)[len(evs) // 2]
+        extra["closed_loop_loss_and_weight_gradient"] = {
+            "value": g.N / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms, "kernels_per_step": 3,
+            "note": "fields (strict MLP, 3 slices) -> residuals + sums -> stencil adjoint + MLP backward; median of 10"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

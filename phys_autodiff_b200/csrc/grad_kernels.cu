@@ -25,7 +25,7 @@ __device__ __forceinline__ f32x2 sub2_rn(f32x2 a, f32x2 b) {
 // the FP32 pipe's issue slots, and a packed instruction retires two lane-operations per slot.  A lane owns
 // PPL pairs; HT/2 pairs span LPP lanes, so a warp takes PPW = 32/LPP points per iteration (2 for HT = 32).
 template <int HT>
-__global__ void __launch_bounds__(GRAD_THREADS, HT <= 64 ? 2 : 1) k_phys_grad(const GradArgs a) {
+__global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a) {
     constexpr int LPP = HT >= 64 ? 32 : HT / 2;
     constexpr int PPL = HT / 2 / LPP;
     constexpr int PPW = 32 / LPP;
@@ -36,6 +36,9 @@ __global__ void __launch_bounds__(GRAD_THREADS, HT <= 64 ? 2 : 1) k_phys_grad(co
     __shared__ float4 s_gd[2][GRAD_THREADS]; // A_+ (= -A_-)
     __shared__ unsigned int s_flag;
     static_assert(sizeof(float4) * 2 * GRAD_THREADS * 3 >= sizeof(double) * NGT, "final sums reuse the staging arrays");
+    // double accumulators of every thread, [accumulator][thread] (conflict-free): registers are better spent on
+    // a third resident block -- the loop is latency-bound at two
+    extern __shared__ double s_dacc[];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int sub = lane / LPP, lp = lane % LPP;
@@ -67,11 +70,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, HT <= 64 ? 2 : 1) k_phys_grad(co
         for (int o = 0; o < 4; ++o)
             w2c[j][o] = pack2(on0 ? __ldg(a.W2 + o * a.H + h0) : 0.f, on1 ? __ldg(a.W2 + o * a.H + h1) : 0.f);
     }
-    double acc[PPL][GRAD_NACC][2];
 #pragma unroll
-    for (int j = 0; j < PPL; ++j)
-#pragma unroll
-        for (int k = 0; k < GRAD_NACC; ++k) acc[j][k][0] = acc[j][k][1] = 0.0;
+    for (int k = 0; k < PPL * GRAD_NACC * 2; ++k) s_dacc[k * GRAD_THREADS + threadIdx.x] = 0.0;
     double db2[4] = {0.0, 0.0, 0.0, 0.0};
 
     int buf = 0;
@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, HT <= 64 ? 2 : 1) k_phys_grad(co
             for (int k = 0; k < GRAD_NACC; ++k) {
                 float lo, hi;
                 unpack2(f[j][k], lo, hi);
-                acc[j][k][0] += double(lo);
-                acc[j][k][1] += double(hi);
+                s_dacc[((j * GRAD_NACC + k) * 2) * GRAD_THREADS + threadIdx.x] += double(lo);
+                s_dacc[((j * GRAD_NACC + k) * 2 + 1) * GRAD_THREADS + threadIdx.x] += double(hi);
             }
     }
 
@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, HT <= 64 ? 2 : 1) k_phys_grad(co
     for (int j = 0; j < PPL; ++j)
 #pragma unroll
         for (int k = 0; k < GRAD_NACC; ++k) {
-            double lo = acc[j][k][0], hi = acc[j][k][1];
+            double lo = s_dacc[((j * GRAD_NACC + k) * 2) * GRAD_THREADS + threadIdx.x];
+            double hi = s_dacc[((j * GRAD_NACC + k) * 2 + 1) * GRAD_THREADS + threadIdx.x];
             if (PPW == 2) {   // the two half-warps hold the same hidden units for different points
                 lo += __shfl_xor_sync(0xffffffffu, lo, 16);
                 hi += __shfl_xor_sync(0xffffffffu, hi, 16);
@@ -289,8 +290,13 @@ __global__ void __launch_bounds__(GRAD_THREADS, HT <= 64 ? 2 : 1) k_phys_grad(co
 
 namespace {
 template <int HT>
+constexpr size_t grad_smem() { return size_t(HT >= 64 ? HT / 64 : 1) * GRAD_NACC * 2 * GRAD_THREADS * sizeof(double); }
+
+template <int HT>
 int blocks_per_sm_t(int* out) {
-    return int(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k_phys_grad<HT>, GRAD_THREADS, 0));
+    cudaError_t e = cudaFuncSetAttribute(k_phys_grad<HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(grad_smem<HT>()));
+    if (e != cudaSuccess) return int(e);
+    return int(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k_phys_grad<HT>, GRAD_THREADS, grad_smem<HT>()));
 }
 }  // namespace
 
@@ -305,9 +311,9 @@ int grad_blocks_per_sm(int HT, int* out) {
 
 int grad_launch(int HT, const GradArgs& a, unsigned blocks, cudaStream_t st) {
     switch (HT) {
-        case 32: k_phys_grad<32><<<blocks, GRAD_THREADS, 0, st>>>(a); break;
-        case 64: k_phys_grad<64><<<blocks, GRAD_THREADS, 0, st>>>(a); break;
-        case 128: k_phys_grad<128><<<blocks, GRAD_THREADS, 0, st>>>(a); break;
+        case 32: k_phys_grad<32><<<blocks, GRAD_THREADS, grad_smem<32>(), st>>>(a); break;
+        case 64: k_phys_grad<64><<<blocks, GRAD_THREADS, grad_smem<64>(), st>>>(a); break;
+        case 128: k_phys_grad<128><<<blocks, GRAD_THREADS, grad_smem<128>(), st>>>(a); break;
         default: return int(cudaErrorInvalidValue);
     }
     return int(cudaGetLastError());
