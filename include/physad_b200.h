@@ -254,6 +254,12 @@ void physad_mlp_random_init(int In, int H, int Out, unsigned int seed, float sca
  * gradient pointer may be null) and replaces the weights first when cfg != NULL. */
 int physad_fused_loss_grad_dev(physad_ctx* ctx, const physad_grid* g, const physad_phys_weights* w, float t, float dt,
                                double* acc, double* grad, void* stream);
+/* One rank's share for multi-GPU: the SUMS over the points of slab [z_begin, z_end) -- acc as above and the partial
+ * gradient (already scaled by 2w/N of the GLOBAL grid) -- so that an all-reduce(sum) of the 9H+6 doubles over the
+ * ranks gives the whole-grid result.  The two residual planes and four field planes around the slab are recomputed
+ * locally from coordinates (no halo exchange).  Empty slab: zeros. */
+int physad_fused_loss_grad_slab_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab,
+                                    const physad_phys_weights* w, float t, float dt, double* acc, double* grad, void* stream);
 int physad_fused_loss_grad_host(physad_ctx* ctx, const physad_grid* g, const physad_mlp_config* cfg, const float* W1,
                                 const float* b1, const float* W2, const float* b2, const physad_phys_weights* w, float t,
                                 float dt, float* loss_sigma, float* loss_u, float* dW1, float* db1, float* dW2, float* db2);

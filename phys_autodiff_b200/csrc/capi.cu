@@ -512,7 +512,7 @@ int launch_grad(physad_ctx* c, int HT, const GradArgs& a, size_t chunks, cudaStr
         if (bps < 1) return fail(PHYSAD_E_UNSUPPORTED, "fused_loss_grad: kernel does not fit an SM");
     }
     const size_t blocks = std::max<size_t>(1, std::min<size_t>(chunks, size_t(c->sm_count) * bps));
-    const size_t need = blocks * (GRAD_NACC * HT + 4);
+    const size_t need = blocks * (GRAD_NACC * HT + 6);
     if (need > c->gpart_cap) {
         if (c->gpart) CU(cudaFree(c->gpart));
         c->gpart = nullptr; c->gpart_cap = 0;
@@ -1148,35 +1148,23 @@ int physad_fused_loss_allreduce_dev(physad_ctx* c, const physad_grid* g, const p
 
 // ---- closed loop: loss and its gradient with respect to the MLP weights (additive, grad_kernels.cuh) ----
 
-int physad_fused_loss_grad_dev(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w, float t, float dt,
-                               double* acc, double* grad, void* stream) {
-    if (!c || !w || !acc || !grad) return fail(PHYSAD_E_INVALID, "fused_loss_grad: null argument");
-    if (int rc = check_grid(g)) return rc;
-    if (int rc = need_4x4(c, "fused_loss_grad")) return rc;
-    DeviceGuard dg(c->device);
-    cudaStream_t st = cudaStream_t(stream);
-    const size_t N = size_t(g->nx) * g->ny * g->nz;
-    if (16 * N > c->gws_cap) {
-        if (c->gws) CU(cudaFree(c->gws));
-        c->gws = nullptr; c->gws_cap = 0;
-        CU(cudaMalloc(&c->gws, 16 * N * sizeof(float)));
-        c->gws_cap = 16 * N;
-    }
-    // forward, stage-wise on the device: fields of the three slices, then residuals + the two sums
-    float* f = c->gws;
-    float *s_m = f, *s_0 = f + N, *s_p = f + 2 * N, *u_m = f + 3 * N, *u_0 = f + 6 * N, *u_p = f + 9 * N, *R = f + 12 * N;
-    if (int rc = physad_mlp_generate_fields_dev(c, g, nullptr, t, dt, s_m, s_0, s_p, u_m, u_0, u_p, stream)) return rc;
-    if (int rc = physad_phys_loss_dev(c, g, s_m, s_0, s_p, u_m, u_0, u_p, acc, R, R + N, R + 2 * N, R + 3 * N, stream)) return rc;
-    // backward
+namespace {
+int ensure_grad_workspace(physad_ctx* c, size_t floats) {
+    if (floats <= c->gws_cap) return 0;
+    if (c->gws) CU(cudaFree(c->gws));
+    c->gws = nullptr; c->gws_cap = 0;
+    CU(cudaMalloc(&c->gws, floats * sizeof(float)));
+    c->gws_cap = floats;
+    return 0;
+}
+
+// the parts of GradArgs that do not depend on where the arrays live
+int grad_args_common(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w, float t, float dt, GradArgs& a,
+                     cudaStream_t st) {
     if (int rc = upload_weights_if_stale(c, st)) return rc;
     if (int rc = ensure_coord_tables(c, g, st)) return rc;
-    GradArgs a{};
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
-    a.z_begin = 0; a.z_end = g->nz; a.z_origin = 0;
-    a.periodic = g->periodic != 0; a.wrap_z = a.periodic;
-    a.cstride = N;
-    a.s0 = s_0; a.u0 = u_0;
-    for (int k = 0; k < 4; ++k) a.R[k] = R + k * N;
+    a.periodic = g->periodic != 0;
     a.cxs = c->tab.dev; a.cys = a.cxs + g->nx; a.czs = a.cys + g->ny;
     vjp_scales(g, w, &a.scale_s, &a.scale_u);
     a.inv2dt = inv2(dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
@@ -1185,9 +1173,93 @@ int physad_fused_loss_grad_dev(physad_ctx* c, const physad_grid* g, const physad
     a.W1 = c->dW1; a.b1 = c->db1; a.W2 = c->dW2;
     a.H = c->cfg.H;
     a.ticket = c->ticket;
+    return 0;
+}
+}  // namespace
+
+int physad_fused_loss_grad_dev(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w, float t, float dt,
+                               double* acc, double* grad, void* stream) {
+    if (!c || !w || !acc || !grad) return fail(PHYSAD_E_INVALID, "fused_loss_grad: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = need_4x4(c, "fused_loss_grad")) return rc;
+    DeviceGuard dg(c->device);
+    cudaStream_t st = cudaStream_t(stream);
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    if (int rc = ensure_grad_workspace(c, 16 * N)) return rc;
+    // forward, stage-wise on the device: fields of the three slices, then residuals + the two sums
+    float* f = c->gws;
+    float *s_m = f, *s_0 = f + N, *s_p = f + 2 * N, *u_m = f + 3 * N, *u_0 = f + 6 * N, *u_p = f + 9 * N, *R = f + 12 * N;
+    if (int rc = physad_mlp_generate_fields_dev(c, g, nullptr, t, dt, s_m, s_0, s_p, u_m, u_0, u_p, stream)) return rc;
+    if (int rc = physad_phys_loss_dev(c, g, s_m, s_0, s_p, u_m, u_0, u_p, acc, R, R + N, R + 2 * N, R + 3 * N, stream)) return rc;
+    // backward
+    GradArgs a{};
+    if (int rc = grad_args_common(c, g, w, t, dt, a, st)) return rc;
+    a.z_begin = 0; a.z_end = g->nz; a.z_origin = 0;
+    a.wrap_z = a.periodic;
+    a.cstride = N;
+    a.s0 = s_0; a.u0 = u_0;
+    for (int k = 0; k < 4; ++k) a.R[k] = R + k * N;
     a.grad = grad;
-    const size_t chunks = (N + GRAD_THREADS - 1) / GRAD_THREADS;
-    return launch_grad(c, template_h(c->cfg.H), a, chunks, st);
+    return launch_grad(c, template_h(c->cfg.H), a, (N + GRAD_THREADS - 1) / GRAD_THREADS, st);
+}
+
+int physad_fused_loss_grad_slab_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab,
+                                    const physad_phys_weights* w, float t, float dt, double* acc, double* grad, void* stream) {
+    if (!c || !w || !acc || !grad || !slab) return fail(PHYSAD_E_INVALID, "fused_loss_grad_slab: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = need_4x4(c, "fused_loss_grad_slab")) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    if (s.z_begin == 0 && s.z_end == g->nz) return physad_fused_loss_grad_dev(c, g, w, t, dt, acc, grad, stream);
+    DeviceGuard dg(c->device);
+    cudaStream_t st = cudaStream_t(stream);
+    const int H = c->cfg.H;
+    if (s.z_begin == s.z_end) {
+        CU(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+        CU(cudaMemsetAsync(grad, 0, size_t(9 * H + 4) * sizeof(double), st));
+        return 0;
+    }
+    // The gradient of the slab's points needs the residuals one plane beyond the slab, hence the fields two planes
+    // beyond it: a window of VIRTUAL planes [zlo, zhi) (wrapped on a periodic grid, cut at the faces otherwise) is
+    // recomputed locally -- no halo exchange, like the forward path.
+    const bool per = g->periodic != 0;
+    const int zlo = per ? s.z_begin - 2 : std::max(0, s.z_begin - 2);
+    const int zhi = per ? s.z_end + 2 : std::min(g->nz, s.z_end + 2);
+    const int npl = zhi - zlo;
+    const size_t pln = size_t(g->nx) * g->ny, NL = pln * npl;
+    if (NL >= (size_t(1) << 31)) return fail(PHYSAD_E_UNSUPPORTED, "fused_loss_grad_slab: window of 2^31 points or more");
+    if (int rc = ensure_grad_workspace(c, 16 * NL)) return rc;
+    float* f = c->gws;
+    float *s_m = f, *s_0 = f + NL, *s_p = f + 2 * NL, *u_m = f + 3 * NL, *u_0 = f + 6 * NL, *u_p = f + 9 * NL, *R = f + 12 * NL;
+    const float ts[3] = {t - dt, t, t + dt};
+    const float tc[3] = {time_coord(ts[0], c->cfg.norm), time_coord(ts[1], c->cfg.norm), time_coord(ts[2], c->cfg.norm)};
+    // fields: one launch per run of consecutive global planes inside the window
+    for (int zv = zlo; zv < zhi;) {
+        const int ga = ((zv % g->nz) + g->nz) % g->nz;
+        const int run = std::min(zhi - zv, g->nz - ga);
+        const size_t off = size_t(zv - zlo) * pln;
+        GridInferArgs ga_args{};
+        ga_args.sigma[0] = s_m + off; ga_args.sigma[1] = s_0 + off; ga_args.sigma[2] = s_p + off;
+        ga_args.u[0] = u_m + off; ga_args.u[1] = u_0 + off; ga_args.u[2] = u_p + off;
+        ga_args.cstride = NL;
+        if (int rc = launch_grid<true>(c, g, physad_slab{ga, ga + run}, tc, ga_args, st)) return rc;
+        zv += run;
+    }
+    // residuals of every plane of the window with the z neighbours clamped at its ends: exact wherever both z
+    // neighbours are inside the window (or the end is a face of a non-periodic grid); the other planes are not used
+    PhysArgs pa = phys_args(s_m, s_0, s_p, u_m, u_0, u_p, R, R + NL, R + 2 * NL, R + 3 * NL);
+    pa.clamp_z = 1;
+    if (int rc = launch_phys<true, false, false>(c, g, pa, st, npl)) return rc;
+    GradArgs a{};
+    if (int rc = grad_args_common(c, g, w, t, dt, a, st)) return rc;
+    a.z_begin = s.z_begin; a.z_end = s.z_end; a.z_origin = zlo;
+    a.wrap_z = 0;
+    a.cstride = NL;
+    a.s0 = s_0; a.u0 = u_0;
+    for (int k = 0; k < 4; ++k) a.R[k] = R + k * NL;
+    a.grad = grad;
+    a.acc_out = acc;
+    return launch_grad(c, template_h(H), a, (pln * size_t(s.z_end - s.z_begin) + GRAD_THREADS - 1) / GRAD_THREADS, st);
 }
 
 int physad_fused_loss_grad_host(physad_ctx* c, const physad_grid* g, const physad_mlp_config* cfg, const float* W1,

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a)
     constexpr int PPL = HT / 2 / LPP;
     constexpr int PPW = 32 / LPP;
     constexpr int NW = GRAD_THREADS / 32;
-    constexpr int NGT = GRAD_NACC * HT + 4;
+    constexpr int NGT = GRAD_NACC * HT + 6;   // accumulators | db2[4] | sum R_sigma^2, sum |R_u|^2
     __shared__ float4 s_x[2][GRAD_THREADS];  // cx, cy, cz, -
     __shared__ float4 s_gt[2][GRAD_THREADS]; // A_t
     __shared__ float4 s_gd[2][GRAD_THREADS]; // A_+ (= -A_-)
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a)
     }
 #pragma unroll
     for (int k = 0; k < PPL * GRAD_NACC * 2; ++k) s_dacc[k * GRAD_THREADS + threadIdx.x] = 0.0;
-    double db2[4] = {0.0, 0.0, 0.0, 0.0};
+    double db2[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // db2[0..3], then the two residual square sums
 
     int buf = 0;
     for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, buf ^= 1) {
@@ -102,8 +102,10 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a)
                                           {size_t(zm - a.z_origin) * plane + size_t(y) * a.nx + x,
                                            size_t(zp - a.z_origin) * plane + size_t(y) * a.nx + x}};
                 const float i2h[3] = {a.inv2hx, a.inv2hy, a.inv2hz};
-                const float gq[4] = {a.scale_s * __ldg(a.R[0] + q), a.scale_u * __ldg(a.R[1] + q),
-                                     a.scale_u * __ldg(a.R[2] + q), a.scale_u * __ldg(a.R[3] + q)};
+                const float rq[4] = {__ldg(a.R[0] + q), __ldg(a.R[1] + q), __ldg(a.R[2] + q), __ldg(a.R[3] + q)};
+                const float gq[4] = {a.scale_s * rq[0], a.scale_u * rq[1], a.scale_u * rq[2], a.scale_u * rq[3]};
+                db2[4] += double(rq[0]) * double(rq[0]);
+                db2[5] += double(rq[1]) * double(rq[1]) + double(rq[2]) * double(rq[2]) + double(rq[3]) * double(rq[3]);
                 float A[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
@@ -241,15 +243,15 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a)
             __syncthreads();
         }
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
+    for (int o = 0; o < 6; ++o) {
         const double v = warp_sum_d(db2[o]);
-        if (lane == 0) s_acc[wid * 4 + o] = v;
+        if (lane == 0) s_acc[wid * 6 + o] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 4) {
+    if (threadIdx.x < 6) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) s += s_acc[w * 4 + threadIdx.x];
+        for (int w = 0; w < NW; ++w) s += s_acc[w * 6 + threadIdx.x];
         part[GRAD_NACC * HT + threadIdx.x] = s;
     }
     __threadfence();
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a)
         }
         a.grad[e] = v;
     }
+    if (a.acc_out && threadIdx.x < 2) a.acc_out[threadIdx.x] = tot[GRAD_NACC * HT + 4 + threadIdx.x];
     if (threadIdx.x == 0) *a.ticket = 0u;
 }
 

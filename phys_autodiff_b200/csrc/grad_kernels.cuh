@@ -41,9 +41,10 @@ struct GradArgs {
     float tc[3];               // network time input of the three slices
     const float *W1, *b1, *W2; // device copies, reference layout
     int H;                     // runtime width (<= template width)
-    double* partials;          // [gridDim.x][GRAD_NACC*HT + 4]
+    double* partials;          // [gridDim.x][GRAD_NACC*HT + 6]
     unsigned int* ticket;
     double* grad;              // [9*H + 4] (runtime H): dW1 | db1 | dW2 | db2
+    double* acc_out;           // optional [2]: sum R_sigma^2, sum |R_u|^2 over the processed points
 };
 
 constexpr int GRAD_THREADS = 256;

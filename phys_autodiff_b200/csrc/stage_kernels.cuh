@@ -25,6 +25,7 @@ struct GridInferArgs {
     float4* out_aos;    // FIELDS=false
     float* sigma[3];    // FIELDS=true: t-dt, t, t+dt
     float* u[3];
+    size_t cstride;     // FIELDS=true: channel stride of the u arrays; 0 = the slab's point count
 };
 
 // Block = 32 x 8 threads on a 32 x 32 (x,y) patch of one z plane; a thread evaluates 4 points that share x
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(256) k_mlp_grid(const __grid_constant__ MlpCon
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y0 = blockIdx.y * 32 + (threadIdx.x >> 5);
     const int z = a.z_begin + blockIdx.z;
-    const size_t n = size_t(a.z_end - a.z_begin) * a.ny * a.nx;
+    const size_t n = a.cstride ? a.cstride : size_t(a.z_end - a.z_begin) * a.ny * a.nx;
     const float cx = __ldg(a.cxs + min(x, a.nx - 1));
     const float cz = __ldg(a.czs + z);
     float cy[P];
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__(256) k_bwd_db(const float* __restrict__ G, flo
 struct PhysArgs {
     int nx, ny, nz;   // nz = number of planes IN THE ARRAYS (the slab's planes in slab mode)
     int periodic;
+    int clamp_z;  // 1: clamp the z neighbours at the ends of the arrays even on a periodic grid (the arrays are a
+                  //    window of planes whose outermost residuals the caller discards, see physad_fused_loss_grad_slab_dev)
     int zc;  // planes per z chunk
     // slab mode (multi-GPU on supplied fields): the arrays hold only this rank's planes, and the time-t planes
     // just below / above the slab ([4 channels][ny][nx] each, already wrapped/clamped by the host) come from
@@ -227,12 +230,12 @@ struct PhysArgs {
 __device__ __forceinline__ const float* plane_below(const PhysArgs& a, const float* f0c, int c, int z, size_t pln, bool per) {
     if (z > 0) return f0c + size_t(z - 1) * pln;
     if (a.halo_lo) return a.halo_lo + size_t(c) * pln;
-    return f0c + size_t(per ? a.nz - 1 : 0) * pln;
+    return f0c + size_t((per && !a.clamp_z) ? a.nz - 1 : 0) * pln;
 }
 __device__ __forceinline__ const float* plane_above(const PhysArgs& a, const float* f0c, int c, int z, size_t pln, bool per) {
     if (z + 1 < a.nz) return f0c + size_t(z + 1) * pln;
     if (a.halo_hi) return a.halo_hi + size_t(c) * pln;
-    return f0c + size_t(per ? 0 : a.nz - 1) * pln;
+    return f0c + size_t((per && !a.clamp_z) ? 0 : a.nz - 1) * pln;
 }
 
 // neighbour index for an offset of +-1 (n >= 1): wrap or clamp without a division

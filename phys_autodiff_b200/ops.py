@@ -366,12 +366,33 @@ class Context:
                                                    ptr(acc), ptr(grad), self._stream()), "fused_loss_grad")
         return acc, grad
 
-    def fused_loss_grad(self, g: Grid, pw: PhysWeights, t: float, dt: float):
-        """(L_sigma, L_u, grad float64 ndarray[9H+4]) of the weights set by set_weights()."""
-        acc, grad = self.fused_loss_grad_acc(g, pw, t, dt)
-        gh = grad.cpu().numpy()
-        ls, lu = self.finalize(self._read_acc(acc), pw, g.N)
-        return ls, lu, gh
+    def fused_loss_grad_slab_acc(self, g: Grid, pw: PhysWeights, t: float, dt: float, slab, out=None):
+        """One slab's SUMS: returns a float64 device tensor [acc_sigma, acc_u, grad(9H+4)] (all-reduce it over ranks)."""
+        import torch
+        out = out if out is not None else self._empty(9 * self.cfg.H + 6, torch.float64)
+        cs, _ = self._slab(g, slab)
+        cg, cw = g.c(), pw.c()
+        check(self._lib.physad_fused_loss_grad_slab_dev(self._h, C.byref(cg), C.byref(cs), C.byref(cw), C.c_float(t),
+                                                        C.c_float(dt), ptr(out), ptr(out[2:]), self._stream()),
+              "fused_loss_grad_slab")
+        return out
+
+    def fused_loss_grad(self, g: Grid, pw: PhysWeights, t: float, dt: float, group=None):
+        """(L_sigma, L_u, grad float64 ndarray[9H+4]) of the weights set by set_weights().  With torch.distributed
+        initialised each rank differentiates its z-slab (fields two planes around it recomputed locally) and ONE
+        all-reduce of 9H+6 doubles combines the sums."""
+        import torch.distributed as dist
+        world, rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_initialized() else (1, 0)
+        if world == 1:
+            acc, grad = self.fused_loss_grad_acc(g, pw, t, dt)
+            gh = grad.cpu().numpy()
+            ls, lu = self.finalize(self._read_acc(acc), pw, g.N)
+            return ls, lu, gh
+        buf = self.fused_loss_grad_slab_acc(g, pw, t, dt, slab_for_rank(g.nz, rank, world))
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        h = buf.cpu().numpy()
+        ls, lu = self.finalize(h[:2], pw, g.N)
+        return ls, lu, h[2:].copy()
 
     def fused_loss_grad_host(self, g: Grid, cfg: MLPConfig, W1, b1, W2, b2, pw: PhysWeights, t: float, dt: float):
         """Host-buffer form: weights in, (L_sigma, L_u, dW1, db1, dW2, db2) out (float32, the reference's layouts)."""

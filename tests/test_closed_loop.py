@@ -116,6 +116,28 @@ def test_gradient_is_deterministic_and_device_form_agrees(ctx, port):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape,per,H", [((40, 24, 13), True, 64), ((40, 24, 13), False, 64), ((33, 9, 3), True, 32),
+                                          ((128, 8, 10), False, 128)])
+def test_slab_gradients_sum_to_the_whole(ctx, port, shape, per, H):
+    """Multi-GPU decomposition on one device: the slab sums (fields two planes around each slab recomputed
+    locally, window wrapped or cut at the faces) add up to the whole-grid loss sums and gradient."""
+    from phys_autodiff_b200 import MLPConfig, PhysWeights
+    from phys_autodiff_b200.ops import slab_for_rank
+    og = OGrid(*shape, 1, 1, 1, 2e-3, per)
+    ctx.set_weights(MLPConfig(4, H, 4, True), *port.mlp_random_init(H, 777, 0.25))
+    pw = PhysWeights(1.3, 0.7)
+    acc, grad = ctx.fused_loss_grad_acc(_g(og), pw, 0.25, 2e-3)
+    whole = np.concatenate([acc.cpu().numpy(), grad.cpu().numpy()])
+    for world in (2, 3, 8):
+        tot = np.zeros_like(whole)
+        for r in range(world):
+            tot += ctx.fused_loss_grad_slab_acc(_g(og), pw, 0.25, 2e-3, slab_for_rank(og.nz, r, world)).cpu().numpy()
+        assert np.abs(tot[:2] - whole[:2]).max() <= 1e-12 * np.abs(whole[:2]).max()
+        # the gradient's fp32 batch sums (32 points each) fall on different points when the slabs start elsewhere
+        assert np.abs(tot[2:] - whole[2:]).max() <= 2e-6 * np.abs(whole[2:]).max(), world
+
+
+@pytest.mark.gpu
 def test_training_reduces_the_loss_by_90_percent(ctx, port):
     """Acceptance criterion of the reference's plan (REQUIREMENT.md:164-169): within K steps L falls >= 90 %."""
     from phys_autodiff_b200 import MLPConfig, PhysWeights

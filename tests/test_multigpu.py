@@ -42,7 +42,12 @@ plane = g.nx * g.ny
 same = all(torch.equal(a, b[z0 * plane:z1 * plane]) for a, b in zip(R, Rw))
 same = same and all(torch.equal(a, b[z0 * plane:z1 * plane]) for a, b in zip(sh[2], Rw))
 l1 = ctx.finalize(whole, PhysWeights(1.3, 0.7), g.N)
-out = dict(rank=rank, sharded=[float(sh[0]), float(sh[1])], p2p=[[float(a), float(b)] for a, b in p2p], ls=float(ls), lu=float(lu), ls1=float(l1[0]), lu1=float(l1[1]), same=bool(same), slab=[z0, z1])
+# closed loop: slab gradients + one all-reduce of 9H+6 doubles == the single-GPU gradient
+gl = ctx.fused_loss_grad(g, PhysWeights(1.3, 0.7), 0.25, 2e-3)
+ga1, gg1 = ctx.fused_loss_grad_acc(g, PhysWeights(1.3, 0.7), 0.25, 2e-3)
+gg1 = gg1.cpu().numpy()
+grad_err = float(np.abs(gl[2] - gg1).max() / np.abs(gg1).max())
+out = dict(grad_err=grad_err, grad_ls=float(gl[0]), grad_lu=float(gl[1]), rank=rank, sharded=[float(sh[0]), float(sh[1])], p2p=[[float(a), float(b)] for a, b in p2p], ls=float(ls), lu=float(lu), ls1=float(l1[0]), lu1=float(l1[1]), same=bool(same), slab=[z0, z1])
 gathered = [None] * world
 dist.all_gather_object(gathered, out)
 if rank == 0:
@@ -75,3 +80,6 @@ def test_two_rank_fused_loss_matches_single_gpu(tmp_path):
         assert abs(d["sharded"][0] - d["ls1"]) <= 1e-6 * abs(d["ls1"]) and abs(d["sharded"][1] - d["lu1"]) <= 1e-6 * abs(d["lu1"])
         assert abs(d["p2p"][0][0] - d["ls"]) <= 1e-6 * abs(d["ls"]) and abs(d["p2p"][0][1] - d["lu"]) <= 1e-6 * abs(d["lu"])
         assert abs(d["ls"] - d["ls1"]) <= 1e-6 * abs(d["ls1"]) and abs(d["lu"] - d["lu1"]) <= 1e-6 * abs(d["lu1"])
+        # closed loop over the ranks == single GPU (different summation order only)
+        assert d["grad_err"] <= 2e-6, d["grad_err"]   # fp32 32-point batch sums fall on different points
+        assert abs(d["grad_ls"] - d["ls1"]) <= 1e-6 * abs(d["ls1"]) and abs(d["grad_lu"] - d["lu1"]) <= 1e-6 * abs(d["lu1"])
