@@ -158,3 +158,32 @@ def test_training_reduces_the_loss_by_90_percent(ctx, port):
         v = 0.999 * v + 0.001 * gvec * gvec
         th = th - 3e-3 * (m / (1 - 0.9 ** k)) / (np.sqrt(v / (1 - 0.999 ** k)) + 1e-8)
     assert np.isfinite(last) and last <= 0.1 * first, (first, last)
+
+
+@pytest.mark.gpu
+def test_gradient_error_paths(port):
+    """Status codes, not crashes: no weights, unsupported shapes, bad slabs, null pointers; empty slab gives zeros."""
+    import ctypes as C
+    from phys_autodiff_b200 import Grid, MLPConfig, PhysadError, PhysWeights, capi, ops
+    c2 = ops.Context()
+    try:
+        g, pw = Grid(8, 8, 8, 1, 1, 1, 1e-3, True), PhysWeights(1, 1)
+        c2.cfg = MLPConfig(4, 16, 4, True)
+        with pytest.raises(PhysadError, match="no weights"):
+            c2.fused_loss_grad_acc(g, pw, 0.1, 1e-3)
+        c2.set_weights(MLPConfig(4, 256, 4, True), *port.mlp_random_init(256, 1, 0.1))
+        with pytest.raises(PhysadError, match="H > 128"):
+            c2.fused_loss_grad_acc(g, pw, 0.1, 1e-3)
+        c2.set_weights(MLPConfig(4, 16, 4, True), *port.mlp_random_init(16, 1, 0.1))
+        with pytest.raises(PhysadError):
+            c2.fused_loss_grad_acc(Grid(0, 8, 8), pw, 0.1, 1e-3)
+        with pytest.raises(PhysadError, match="slab"):
+            c2.fused_loss_grad_slab_acc(g, pw, 0.1, 1e-3, (4, 12))
+        z = c2.fused_loss_grad_slab_acc(g, pw, 0.1, 1e-3, (3, 3)).cpu().numpy()
+        assert z.shape == (9 * 16 + 6,) and not z.any()
+        lib = capi.lib()
+        assert lib.physad_fused_loss_grad_dev(c2._h, None, None, C.c_float(0), C.c_float(0), None, None, None) != 0
+        assert lib.physad_fused_loss_grad_host(None, None, None, None, None, None, None, None, C.c_float(0), C.c_float(0),
+                                               None, None, None, None, None, None) != 0
+    finally:
+        c2.close()
