@@ -505,7 +505,7 @@ struct DeviceGuard {
 }  // namespace
 
 namespace {
-int launch_grad(physad_ctx* c, int HT, const GradArgs& a, size_t chunks, cudaStream_t st) {
+int launch_grad(physad_ctx* c, int HT, const GradArgs& a, float4* adj, size_t chunks, cudaStream_t st) {
     int& bps = c->grad_blocks_per_sm[HT == 32 ? 0 : (HT == 64 ? 1 : 2)];
     if (!bps) {
         CU(cudaError_t(grad_blocks_per_sm(HT, &bps)));
@@ -521,8 +521,9 @@ int launch_grad(physad_ctx* c, int HT, const GradArgs& a, size_t chunks, cudaStr
     }
     GradArgs k = a;
     k.partials = c->gpart;
-    c->launches++;
-    CU(cudaError_t(grad_launch(HT, k, unsigned(blocks), st)));
+    c->launches += 2;
+    CU(cudaError_t(adjoint_launch(k, adj, st)));
+    CU(cudaError_t(grad_launch(HT, k, adj, unsigned(blocks), st)));
     return 0;
 }
 }  // namespace
@@ -1185,7 +1186,7 @@ int physad_fused_loss_grad_dev(physad_ctx* c, const physad_grid* g, const physad
     DeviceGuard dg(c->device);
     cudaStream_t st = cudaStream_t(stream);
     const size_t N = size_t(g->nx) * g->ny * g->nz;
-    if (int rc = ensure_grad_workspace(c, 16 * N)) return rc;
+    if (int rc = ensure_grad_workspace(c, 20 * N)) return rc;   // 12 N fields, 4 N residuals, 4 N time-t adjoint
     // forward, stage-wise on the device: fields of the three slices, then residuals + the two sums
     float* f = c->gws;
     float *s_m = f, *s_0 = f + N, *s_p = f + 2 * N, *u_m = f + 3 * N, *u_0 = f + 6 * N, *u_p = f + 9 * N, *R = f + 12 * N;
@@ -1200,7 +1201,7 @@ int physad_fused_loss_grad_dev(physad_ctx* c, const physad_grid* g, const physad
     a.s0 = s_0; a.u0 = u_0;
     for (int k = 0; k < 4; ++k) a.R[k] = R + k * N;
     a.grad = grad;
-    return launch_grad(c, template_h(c->cfg.H), a, (N + GRAD_THREADS - 1) / GRAD_THREADS, st);
+    return launch_grad(c, template_h(c->cfg.H), a, reinterpret_cast<float4*>(f + 16 * N), (N + GRAD_THREADS - 1) / GRAD_THREADS, st);
 }
 
 int physad_fused_loss_grad_slab_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab,
@@ -1228,7 +1229,7 @@ int physad_fused_loss_grad_slab_dev(physad_ctx* c, const physad_grid* g, const p
     const int npl = zhi - zlo;
     const size_t pln = size_t(g->nx) * g->ny, NL = pln * npl;
     if (NL >= (size_t(1) << 31)) return fail(PHYSAD_E_UNSUPPORTED, "fused_loss_grad_slab: window of 2^31 points or more");
-    if (int rc = ensure_grad_workspace(c, 16 * NL)) return rc;
+    if (int rc = ensure_grad_workspace(c, 20 * NL)) return rc;
     float* f = c->gws;
     float *s_m = f, *s_0 = f + NL, *s_p = f + 2 * NL, *u_m = f + 3 * NL, *u_0 = f + 6 * NL, *u_p = f + 9 * NL, *R = f + 12 * NL;
     const float ts[3] = {t - dt, t, t + dt};
@@ -1259,7 +1260,7 @@ int physad_fused_loss_grad_slab_dev(physad_ctx* c, const physad_grid* g, const p
     for (int k = 0; k < 4; ++k) a.R[k] = R + k * NL;
     a.grad = grad;
     a.acc_out = acc;
-    return launch_grad(c, template_h(H), a, (pln * size_t(s.z_end - s.z_begin) + GRAD_THREADS - 1) / GRAD_THREADS, st);
+    return launch_grad(c, template_h(H), a, reinterpret_cast<float4*>(f + 16 * NL), (pln * size_t(s.z_end - s.z_begin) + GRAD_THREADS - 1) / GRAD_THREADS, st);
 }
 
 int physad_fused_loss_grad_host(physad_ctx* c, const physad_grid* g, const physad_mlp_config* cfg, const float* W1,

@@ -52,6 +52,7 @@ constexpr int GRAD_NACC = 10;   // per hidden unit: sum dz*x, dz*y, dz*z | sum d
 
 // grad_kernels.cu (its own translation unit, so the kernel can be rebuilt without the rest of the library)
 int grad_blocks_per_sm(int HT, int* out);                                   // resident blocks per SM on the current device
-int grad_launch(int HT, const GradArgs& a, unsigned blocks, cudaStream_t st);   // returns a cudaError_t value
+int adjoint_launch(const GradArgs& a, float4* adj, cudaStream_t st);        // A_t of every processed point -> adj
+int grad_launch(int HT, const GradArgs& a, const float4* adj, unsigned blocks, cudaStream_t st);   // cudaError_t values
 
 }  // namespace physad
