@@ -233,70 +233,91 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a,
                     P2[j] = mul2_rn(w2s[j], bcast2(xrow.z));
                 }
             }
-#pragma unroll 2
-            for (int i = 0; i < 32 / PPW; ++i) {
-                const int pi = wid * 32 + i * PPW + sub;
-                const float4 xc = s_x[buf][pi];
-                const float4 gt = s_gt[buf][pi];
-                const float4 gd = s_gd[buf][pi];
-                const f32x2 cx2 = bcast2(xc.x), cy2 = bcast2(xc.y), cz2 = bcast2(xc.z);
+            // U points per group: everything up to the mask test for all of them, ONE vote, then the masked part --
+            // so that the branch does not separate the points' independent dependency chains
+            constexpr int U = PPL == 1 ? 2 : 1;
+#pragma unroll 1
+            for (int i = 0; i < 32 / PPW; i += U) {
+                float tl[U][PPL], th[U][PPL], dl[U][PPL], dh[U][PPL], z0l[U][PPL], z0h[U][PPL], cxs[U];
+                bool pml[U][PPL], pmh[U][PPL], ppl[U][PPL], pph[U][PPL];
+                f32x2 cy2[U], cz2[U];
+                bool mixed = false;
 #pragma unroll
-                for (int j = 0; j < PPL; ++j) {
-                    // the forward's operation order, two hidden units at a time:
-                    // ((b1 + W1[h,0] x) + W1[h,1] y) + W1[h,2] z, then + (W1[h,3] t_s rounded)
-                    f32x2 pre = add2_rn_swapped(b1p[j], mul2_rn(w0s[j], cx2));
-                    pre = add2_rn_swapped(pre, ROWB ? P1[j] : mul2_rn(w1s[j], cy2));
-                    pre = add2_rn_swapped(pre, ROWB ? P2[j] : mul2_rn(w2s[j], cz2));
-                    const f32x2 zm = add2_rn(pre, ptm[j]), z0 = add2_rn(pre, pt0[j]), zp = add2_rn(pre, ptp[j]);
-                    float zml, zmh, z0l, z0h, zpl, zph;
-                    unpack2(zm, zml, zmh); unpack2(z0, z0l, z0h); unpack2(zp, zpl, zph);
-                    const f32x2 am = pack2(fmaxf(zml, 0.f), fmaxf(zmh, 0.f));
-                    const f32x2 a0 = pack2(fmaxf(z0l, 0.f), fmaxf(z0h, 0.f));
-                    const f32x2 ap = pack2(fmaxf(zpl, 0.f), fmaxf(zph, 0.f));
-                    // W2^T A for the time-t adjoint and for A_+ (A_- = -A_+)
-                    f32x2 dat = mul2_rn(w2c[j][0], bcast2(gt.x));
-                    dat = fma2_rn(w2c[j][1], bcast2(gt.y), dat);
-                    dat = fma2_rn(w2c[j][2], bcast2(gt.z), dat);
-                    dat = fma2_rn(w2c[j][3], bcast2(gt.w), dat);
-                    f32x2 dad = mul2_rn(w2c[j][0], bcast2(gd.x));
-                    dad = fma2_rn(w2c[j][1], bcast2(gd.y), dad);
-                    dad = fma2_rn(w2c[j][2], bcast2(gd.z), dad);
-                    dad = fma2_rn(w2c[j][3], bcast2(gd.w), dad);
-                    const f32x2 ad = sub2_rn(ap, am);
-                    f[j][6] = fma2_rn(bcast2(gd.x), ad, fma2_rn(bcast2(gt.x), a0, f[j][6]));
-                    f[j][7] = fma2_rn(bcast2(gd.y), ad, fma2_rn(bcast2(gt.y), a0, f[j][7]));
-                    f[j][8] = fma2_rn(bcast2(gd.z), ad, fma2_rn(bcast2(gt.z), a0, f[j][8]));
-                    f[j][9] = fma2_rn(bcast2(gd.w), ad, fma2_rn(bcast2(gt.w), a0, f[j][9]));
-                    float tl, th, dl, dh;
-                    unpack2(dat, tl, th); unpack2(dad, dl, dh);
-                    // z_-, z_0, z_+ are monotone in the slice (a rounded constant is added to the same prefix), so the
-                    // three ReLU masks are equal iff the outer two are.  Warp-uniform fast path for that case
-                    // (all but ~1e-3 of the units at dt = 2e-3): dz_+ + dz_- = 0 and one mask serves all slices.
-                    const bool pml = zml > 0.f, pmh = zmh > 0.f, ppl = zpl > 0.f, pph = zph > 0.f;
-                    if (!__any_sync(0xffffffffu, (pml != ppl) || (pmh != pph))) {
-                        const f32x2 dz0 = pack2(ppl ? tl : 0.f, pph ? th : 0.f);
-                        const f32x2 dzd = pack2(ppl ? dl : 0.f, pph ? dh : 0.f);   // dz_+ = -dz_-
-                        f[j][0] = fma2_rn(dz0, cx2, f[j][0]);
-                        if (!ROWB) {
-                            f[j][1] = fma2_rn(dz0, cy2, f[j][1]);
-                            f[j][2] = fma2_rn(dz0, cz2, f[j][2]);
-                        }
-                        f[j][4] = add2_rn(f[j][4], dz0);
-                        fD[j] = add2_rn(fD[j], dzd);
-                    } else {
-                        const f32x2 dz0 = pack2(z0l > 0.f ? tl : 0.f, z0h > 0.f ? th : 0.f);
-                        const f32x2 dzp = pack2(ppl ? dl : 0.f, pph ? dh : 0.f);
-                        const f32x2 dzm = pack2(pml ? -dl : 0.f, pmh ? -dh : 0.f);
-                        const f32x2 dzs = add2_rn(add2_rn(dz0, dzp), dzm);
-                        f[j][0] = fma2_rn(dzs, cx2, f[j][0]);
-                        if (!ROWB) {
-                            f[j][1] = fma2_rn(dzs, cy2, f[j][1]);
-                            f[j][2] = fma2_rn(dzs, cz2, f[j][2]);
-                        }
-                        f[j][3] = add2_rn(f[j][3], dzm);
-                        f[j][4] = add2_rn(f[j][4], dz0);
-                        f[j][5] = add2_rn(f[j][5], dzp);
+                for (int u = 0; u < U; ++u) {
+                    const int pi = wid * 32 + (i + u) * PPW + sub;
+                    const float4 xc = s_x[buf][pi];
+                    const float4 gt = s_gt[buf][pi];
+                    const float4 gd = s_gd[buf][pi];
+                    const f32x2 cx2 = bcast2(xc.x);
+                    cxs[u] = xc.x; cy2[u] = bcast2(xc.y); cz2[u] = bcast2(xc.z);
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j) {
+                        // the forward's operation order, two hidden units at a time:
+                        // ((b1 + W1[h,0] x) + W1[h,1] y) + W1[h,2] z, then + (W1[h,3] t_s rounded)
+                        f32x2 pre = add2_rn_swapped(b1p[j], mul2_rn(w0s[j], cx2));
+                        pre = add2_rn_swapped(pre, ROWB ? P1[j] : mul2_rn(w1s[j], cy2[u]));
+                        pre = add2_rn_swapped(pre, ROWB ? P2[j] : mul2_rn(w2s[j], cz2[u]));
+                        const f32x2 zm = add2_rn(pre, ptm[j]), z0 = add2_rn(pre, pt0[j]), zp = add2_rn(pre, ptp[j]);
+                        float zml, zmh, zpl, zph;
+                        unpack2(zm, zml, zmh); unpack2(z0, z0l[u][j], z0h[u][j]); unpack2(zp, zpl, zph);
+                        const f32x2 am = pack2(fmaxf(zml, 0.f), fmaxf(zmh, 0.f));
+                        const f32x2 a0 = pack2(fmaxf(z0l[u][j], 0.f), fmaxf(z0h[u][j], 0.f));
+                        const f32x2 ap = pack2(fmaxf(zpl, 0.f), fmaxf(zph, 0.f));
+                        // W2^T A for the time-t adjoint and for A_+ (A_- = -A_+)
+                        f32x2 dat = mul2_rn(w2c[j][0], bcast2(gt.x));
+                        dat = fma2_rn(w2c[j][1], bcast2(gt.y), dat);
+                        dat = fma2_rn(w2c[j][2], bcast2(gt.z), dat);
+                        dat = fma2_rn(w2c[j][3], bcast2(gt.w), dat);
+                        f32x2 dad = mul2_rn(w2c[j][0], bcast2(gd.x));
+                        dad = fma2_rn(w2c[j][1], bcast2(gd.y), dad);
+                        dad = fma2_rn(w2c[j][2], bcast2(gd.z), dad);
+                        dad = fma2_rn(w2c[j][3], bcast2(gd.w), dad);
+                        const f32x2 ad = sub2_rn(ap, am);
+                        f[j][6] = fma2_rn(bcast2(gd.x), ad, fma2_rn(bcast2(gt.x), a0, f[j][6]));
+                        f[j][7] = fma2_rn(bcast2(gd.y), ad, fma2_rn(bcast2(gt.y), a0, f[j][7]));
+                        f[j][8] = fma2_rn(bcast2(gd.z), ad, fma2_rn(bcast2(gt.z), a0, f[j][8]));
+                        f[j][9] = fma2_rn(bcast2(gd.w), ad, fma2_rn(bcast2(gt.w), a0, f[j][9]));
+                        unpack2(dat, tl[u][j], th[u][j]); unpack2(dad, dl[u][j], dh[u][j]);
+                        pml[u][j] = zml > 0.f; pmh[u][j] = zmh > 0.f; ppl[u][j] = zpl > 0.f; pph[u][j] = zph > 0.f;
+                        mixed = mixed || (pml[u][j] != ppl[u][j]) || (pmh[u][j] != pph[u][j]);
                     }
+                }
+                // z_-, z_0, z_+ are monotone in the slice (a rounded constant is added to the same prefix), so the
+                // three ReLU masks are equal iff the outer two are.  Warp-uniform fast path for that case
+                // (all but ~1e-3 of the units at dt = 2e-3): dz_+ + dz_- = 0 and one mask serves all slices.
+                if (!__any_sync(0xffffffffu, mixed)) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int j = 0; j < PPL; ++j) {
+                            const f32x2 dz0 = pack2(ppl[u][j] ? tl[u][j] : 0.f, pph[u][j] ? th[u][j] : 0.f);
+                            const f32x2 dzd = pack2(ppl[u][j] ? dl[u][j] : 0.f, pph[u][j] ? dh[u][j] : 0.f);   // dz_+ = -dz_-
+                            f[j][0] = fma2_rn(dz0, bcast2(cxs[u]), f[j][0]);
+                            if (!ROWB) {
+                                f[j][1] = fma2_rn(dz0, cy2[u], f[j][1]);
+                                f[j][2] = fma2_rn(dz0, cz2[u], f[j][2]);
+                            }
+                            f[j][4] = add2_rn(f[j][4], dz0);
+                            fD[j] = add2_rn(fD[j], dzd);
+                        }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int j = 0; j < PPL; ++j) {
+                            const f32x2 dz0 = pack2(z0l[u][j] > 0.f ? tl[u][j] : 0.f, z0h[u][j] > 0.f ? th[u][j] : 0.f);
+                            const f32x2 dzp = pack2(ppl[u][j] ? dl[u][j] : 0.f, pph[u][j] ? dh[u][j] : 0.f);
+                            const f32x2 dzm = pack2(pml[u][j] ? -dl[u][j] : 0.f, pmh[u][j] ? -dh[u][j] : 0.f);
+                            const f32x2 dzs = add2_rn(add2_rn(dz0, dzp), dzm);
+                            f[j][0] = fma2_rn(dzs, bcast2(cxs[u]), f[j][0]);
+                            if (!ROWB) {
+                                f[j][1] = fma2_rn(dzs, cy2[u], f[j][1]);
+                                f[j][2] = fma2_rn(dzs, cz2[u], f[j][2]);
+                            }
+                            f[j][3] = add2_rn(f[j][3], dzm);
+                            f[j][4] = add2_rn(f[j][4], dz0);
+                            f[j][5] = add2_rn(f[j][5], dzp);
+                        }
                 }
             }
 #pragma unroll
