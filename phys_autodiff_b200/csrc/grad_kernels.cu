@@ -1,4 +1,4 @@
-// The backward kernel of the closed loop; see grad_kernels.cuh for what it computes.
+// The two backward kernels of the closed loop; see grad_kernels.cuh for what they compute.
 #include "grad_kernels.cuh"
 #include "mlp_eval.cuh"
 
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a,
     __shared__ float4 s_gd[2][GRAD_THREADS]; // A_+ (= -A_-)
     __shared__ unsigned int s_flag;
     static_assert(sizeof(float4) * 2 * GRAD_THREADS * 3 >= sizeof(double) * NGT, "final sums reuse the staging arrays");
-    // double accumulators of every thread, [accumulator][thread] (conflict-free): registers are better spent on
-    // a third resident block -- the loop is latency-bound at two
+    // double accumulators of every thread, [accumulator][thread] (conflict-free): 40-80 registers per thread saved,
+    // which is what lets two blocks per SM stay resident at every width
     extern __shared__ double s_dacc[];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

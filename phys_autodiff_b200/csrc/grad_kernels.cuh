@@ -4,21 +4,22 @@
 // reference counterpart, checked against oracle_grad.c (itself pinned by finite differences).
 //
 // Inputs are what the forward pass left in HBM: the time-t fields (sigma, u channel-major) and the four
-// residual arrays.  For every grid point q the kernel
-//   A. forms the adjoint of the three network evaluations at q (thread per point):
+// residual arrays.  Two kernels (grad_kernels.cu):
+//   k_phys_adjoint  forms, for every grid point q, the adjoint of the time-t network outputs:
 //        g      = (2 w / float(N)) * R                         (fp32, as src/phys_cpu.cpp:162-163)
-//        A_+    = +g / (2 dt),  A_- = -g / (2 dt)               (time slices t+dt, t-dt: local)
 //        A_t[c] = local terms  g_s div(u), g_s d_j sigma + sum_i g_ui d_j u_i
 //               + TRANSPOSED central differences of the fluxes  g_s u_j,  g_ui u_j + delta_ij g_s sigma
 //                 taken from the six neighbours (clamped edges: the edge point is its own neighbour and
 //                 the 1/(2h) divisor stays, src/phys_cpu.cpp:8-10, so its flux enters with the sign flipped);
-//   B. back-propagates A through the two-layer ReLU MLP (lane per hidden unit, warp per point): the hidden
-//      pre-activation is recomputed with the forward's exact fp32 operation order (same ReLU mask and
-//      activations as the fields that produced R), everything downstream uses FMAs.  A_+ = -A_- lets the
-//      two outer slices share W2^T A and the dW2 update  A_d (a_+ - a_-).
-// Weight-gradient accumulators live in registers (9 per hidden unit: dW1[h,0..3], db1[h], dW2[0..3,h]),
-// fp32 within a 32-point batch, double across batches; blocks write double partials and the last block
-// to finish sums them in block order (deterministic).
+//   k_phys_grad     back-propagates A_t and A_+ = +g / (2 dt), A_- = -A_+ (time slices t+dt, t-dt: local) through
+//      the two-layer ReLU MLP (lane per PAIR of hidden units, warp per point): the hidden pre-activation is
+//      recomputed with the forward's exact fp32 operation order (same ReLU mask and activations as the fields
+//      that produced R), everything downstream uses packed FMAs.  A_+ = -A_- lets the two outer slices share
+//      W2^T A and the dW2 update  A_+ (a_+ - a_-).
+// Weight-gradient accumulators: ten per hidden unit (sum dz*x, dz*y, dz*z | sum dz_-, dz_0, dz_+ | sum A_o a),
+// fp32 within a 32-point batch, double across batches (per thread, in shared memory); blocks write double
+// partials and the last block to finish sums them in block order (deterministic) and forms
+// dW1[h,3] = sum_s t_s sum dz_s,  db1[h] = sum_s sum dz_s.
 #pragma once
 #include <cuda_runtime.h>
 
