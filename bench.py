@@ -402,8 +402,8 @@ def main():
         torch.cuda.synchronize()
         gms = sorted(e0.elapsed_time(e1) for e0, e1 in evs)[len(evs) // 2]
         extra["closed_loop_loss_and_weight_gradient"] = {
-            "value": g.N / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms, "kernels_per_step": 3,
-            "note": "fields (strict MLP, 3 slices) -> residuals + sums -> stencil adjoint + MLP backward; median of 10"}
+            "value": g.N / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms, "kernels_per_step": 4,
+            "note": "fields (strict MLP, 3 slices) -> residuals + sums -> stencil adjoint -> MLP backward; median of 10"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
