@@ -437,8 +437,8 @@ int launch_phys(physad_ctx* c, const physad_grid* g_in, PhysArgs a, cudaStream_t
     for (const void* p : ptrs) v4 = v4 && (uintptr_t(p) % 16 == 0);
     v4 = v4 && (size_t(g->nx) * g->ny * g->nz) % 4 == 0;  // channel stride of the u arrays
     if (v4) {
-        const unsigned tx = unsigned((g->nx + 255) / 256), ty = unsigned((g->ny + 3) / 4);
-        if (ty > 65535u) return fail(PHYSAD_E_UNSUPPORTED, "phys kernels: ny > 262140");
+        const unsigned tx = unsigned((g->nx + 255) / 256), ty = unsigned((g->ny + V4_THREADS / 64 - 1) / (V4_THREADS / 64));
+        if (ty > 65535u) return fail(PHYSAD_E_UNSUPPORTED, "phys kernels: ny > 131070");
         const long long want = (long long)c->sm_count * 8;
         long long nch = std::max(1LL, std::min<long long>(g->nz, (want + (long long)tx * ty - 1) / ((long long)tx * ty)));
         a.zc = int((g->nz + nch - 1) / nch);
@@ -449,8 +449,8 @@ int launch_phys(physad_ctx* c, const physad_grid* g_in, PhysArgs a, cudaStream_t
             if (int rc = ensure_partials(c, size_t(tx) * ty * nch)) return rc;
             a.partials = c->partials; a.ticket = c->ticket;
         }
-        if (c->exact_residuals) k_phys_residual_v4<WRITE_R, REDUCE, SCALE, true><<<grid, 256, 0, st>>>(a);
-        else k_phys_residual_v4<WRITE_R, REDUCE, SCALE, false><<<grid, 256, 0, st>>>(a);
+        if (c->exact_residuals) k_phys_residual_v4<WRITE_R, REDUCE, SCALE, true><<<grid, V4_THREADS, 0, st>>>(a);
+        else k_phys_residual_v4<WRITE_R, REDUCE, SCALE, false><<<grid, V4_THREADS, 0, st>>>(a);
         c->launches++;
         CU(cudaGetLastError());
         return 0;

@@ -329,20 +329,21 @@ __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
 // for the y neighbours (L1/L2 hits) and 8 scalar loads for the two x neighbours outside its quad, instead of
 // 28 scalar loads per point: 3.7x fewer load instructions and 4x the bytes in flight per thread, which is
 // what the latency-bound scalar form lacks.  Needs nx % 4 == 0 and 16-byte aligned arrays (capi.cu checks
-// and otherwise uses k_phys_residual).  Block = 64 quads (256 columns) x 4 rows.
+// and otherwise uses k_phys_residual).  Block = 64 quads (256 columns) x 2 rows (V4_THREADS = 128).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
+constexpr int V4_THREADS = 128;   // 64 quads x 2 rows: ~170 registers per thread, so three small blocks fit an SM where one of 256 did
 template <bool WRITE_R, bool REDUCE, bool SCALE, bool DPRES>
-__global__ void __launch_bounds__(256) k_phys_residual_v4(const PhysArgs a) {
+__global__ void __launch_bounds__(V4_THREADS, DPRES ? 2 : 3) k_phys_residual_v4(const PhysArgs a) {
     using real = typename std::conditional<DPRES, double, float>::type;
     const real i2t = DPRES ? real(a.inv2dt_d) : real(a.inv2dt), i2x = DPRES ? real(a.inv2hx_d) : real(a.inv2hx);
     const real i2y = DPRES ? real(a.inv2hy_d) : real(a.inv2hy), i2z = DPRES ? real(a.inv2hz_d) : real(a.inv2hz);
-    __shared__ double2 s_red[8];
+    __shared__ double2 s_red[V4_THREADS / 32];
     __shared__ unsigned int s_flag;
     const bool per = a.periodic != 0;
-    const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * (V4_THREADS / 64) + (threadIdx.x >> 6);
     const int z0 = blockIdx.z * a.zc, z1 = min(a.nz, z0 + a.zc);
     const size_t N = size_t(a.nx) * a.ny * a.nz, pln = size_t(a.nx) * a.ny;
     double acc_s = 0.0, acc_u = 0.0;
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(256) k_phys_residual_v4(const PhysArgs a) {
     if (REDUCE) {
         const unsigned int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         const unsigned int nblk = gridDim.x * gridDim.y * gridDim.z;
-        grid_reduce2_lin<8>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag, lin, nblk);
+        grid_reduce2_lin<V4_THREADS / 32>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag, lin, nblk);
     }
 }
 
