@@ -38,11 +38,13 @@ __device__ __forceinline__ void load_q(const float* p, float (&v)[QV]) {
     }
 }
 
+constexpr int ADJ_THREADS = 128;
+
 template <int QV>
-__global__ void __launch_bounds__(256, QV == 4 ? 2 : 4) k_phys_adjoint(const GradArgs a, float4* __restrict__ adj) {
+__global__ void __launch_bounds__(ADJ_THREADS, QV == 4 ? 5 : 8) k_phys_adjoint(const GradArgs a, float4* __restrict__ adj) {
     const int nxq = a.nx / QV;
     const size_t nquads = size_t(nxq) * a.ny * (a.z_end - a.z_begin);
-    const size_t t = size_t(blockIdx.x) * 256 + threadIdx.x;
+    const size_t t = size_t(blockIdx.x) * ADJ_THREADS + threadIdx.x;
     if (t >= nquads) return;
     const int x = int(t % nxq) * QV;
     const size_t r = t / nxq;
@@ -457,8 +459,8 @@ int adjoint_launch(const GradArgs& a, float4* adj, cudaStream_t st) {
     bool v4 = a.nx % 4 == 0 && a.cstride % 4 == 0;
     const void* ptrs[6] = {a.s0, a.u0, a.R[0], a.R[1], a.R[2], a.R[3]};
     for (const void* p : ptrs) v4 = v4 && reinterpret_cast<uintptr_t>(p) % 16 == 0;
-    if (v4) k_phys_adjoint<4><<<unsigned((pts / 4 + 255) / 256), 256, 0, st>>>(a, adj);
-    else k_phys_adjoint<1><<<unsigned((pts + 255) / 256), 256, 0, st>>>(a, adj);
+    if (v4) k_phys_adjoint<4><<<unsigned((pts / 4 + ADJ_THREADS - 1) / ADJ_THREADS), ADJ_THREADS, 0, st>>>(a, adj);
+    else k_phys_adjoint<1><<<unsigned((pts + ADJ_THREADS - 1) / ADJ_THREADS), ADJ_THREADS, 0, st>>>(a, adj);
     return int(cudaGetLastError());
 }
 
