@@ -247,8 +247,8 @@ void physad_mlp_random_init(int In, int H, int Out, unsigned int seed, float sca
  * src/phys_cpu.cpp:151-170, and its MLP backward is the MSE one, src/mlp_cpu.cpp:38-85) ----------------
  * Loss of the MLP-generated fields AND the gradient of L_sigma + L_u (weights w included, mean over N) with
  * respect to the MLP weights set by physad_set_weights: forward stage-wise on the device (fields of the three
- * slices and residuals kept in a context-owned workspace of 64 B/point), then one backward kernel that
- * transposes the stencil and back-propagates through the MLP.  acc: 2 device doubles (sum R_sigma^2, sum |R_u|^2,
+ * slices, residuals and the stencil adjoint kept in a context-owned workspace of 80 B/point), then two backward
+ * kernels: the transposed stencil, and the back-propagation through the MLP with the weight-gradient reduction.  acc: 2 device doubles (sum R_sigma^2, sum |R_u|^2,
  * see physad_finalize_loss); grad: 9H+4 device doubles laid out  dW1[H*4] | db1[H] | dW2[4*H] | db2[4]  (the
  * reference's W1/b1/W2/b2 layouts).  Whole grid on one GPU.  The host form takes/returns host buffers (any
  * gradient pointer may be null) and replaces the weights first when cfg != NULL. */
