@@ -72,6 +72,9 @@ GPU_CASES = [
     ((33, 18, 7), 64, True, False, (1, 1, 1), 2e-3),
     ((70, 37, 5), 128, False, True, (1, 1, 1), 2e-3),
     ((20, 9, 4), 48, True, True, (1, 1, 1), 2e-3),      # padded width
+    ((128, 20, 9), 32, True, True, (1, 1, 1), 2e-3),    # wide rows, row-aligned batches
+    ((256, 6, 5), 16, False, True, (0.5, 1, 2), 2e-3),  # wide rows, clamped faces, anisotropic spacing
+    ((132, 7, 3), 16, False, False, (1, 1, 1), 2e-3),   # wide rows, nx % 32 != 0
     ((5, 3, 2), 16, True, True, (1, 1, 1), 2e-3),
     ((1, 1, 1), 16, True, True, (1, 1, 1), 2e-3),
     ((2, 1, 3), 16, False, True, (1, 1, 1), 2e-3),
