@@ -14,9 +14,9 @@ import json, os, sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-import oracle  # noqa: E402  (a study tool, not the product)
+import oracle  # noqa: E402  (test infrastructure: this study lives under tests/ because it uses the checker)
 from oracle import Grid  # noqa: E402
 
 
