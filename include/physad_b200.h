@@ -40,7 +40,8 @@ enum {
     PHYSAD_OK = 0,
     PHYSAD_E_INVALID = -1,     /* bad argument (null pointer, non-positive size, ...) */
     PHYSAD_E_UNSUPPORTED = -2, /* shape outside what the kernels are built for */
-    PHYSAD_E_NOWEIGHTS = -3    /* context has no weights yet */
+    PHYSAD_E_NOWEIGHTS = -3,   /* context has no weights yet */
+    PHYSAD_E_PEER_TIMEOUT = -4 /* in-kernel multi-GPU exchange: a peer rank never arrived */
 };
 
 /* phys::GridSpec, include/phys.h:8-13 (bool widened to int for C). */
@@ -214,18 +215,25 @@ int physad_fused_loss_host(physad_ctx* ctx, const physad_grid* g, const physad_m
  *   3. every rank: physad_xchg_connect(ctx, rank, world, handles)   -- handles: world x 64 bytes, in rank order
  * Then physad_fused_loss_allreduce_dev behaves like physad_fused_loss_dev, except that acc_dev
  * receives the GLOBAL sums on every rank (added in rank order: identical bits everywhere).  All ranks
- * must make the same sequence of these calls (one exchange epoch per call), slab empty or not.  A rank
- * that never arrives makes the others return NaN after ~4 s instead of hanging. */
+ * must make the same sequence of these calls (one exchange epoch per call), slab empty or not.
+ * CO-RESIDENCY: the exchanging kernels of all ranks wait for each other, so they must be able to run at the
+ * same time -- one process per GPU, each rank launching on its own device (never two ranks' kernels queued
+ * behind each other on one device or one stream).  A rank that never arrives makes the others give up after
+ * ~4 s instead of hanging: their sums become NaN, physad_xchg_status() reports it, and the host one-call
+ * form (physad_fused_loss_slab_host) returns PHYSAD_E_PEER_TIMEOUT. */
 #define PHYSAD_XCHG_HANDLE_BYTES 64
 int physad_xchg_export(physad_ctx* ctx, void* handle_out);
 int physad_xchg_connect(physad_ctx* ctx, int rank, int world, const void* handles);
 int physad_xchg_disconnect(physad_ctx* ctx);
 int physad_fused_loss_allreduce_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float dt,
                                     double* acc_dev, float* R_sigma, float* R_ux, float* R_uy, float* R_uz, void* stream);
+/* Synchronises the device, then *timed_out = 1 if any exchange since the last call gave up waiting for a peer
+ * (and clears the flag), else 0. */
+int physad_xchg_status(physad_ctx* ctx, int* timed_out);
 
 /* One rank's whole step with host buffers in ONE call: (optionally) take new weights from the host,
- * run the fused kernel on `slab` (NULL = whole grid), read the 16-byte result back through pinned memory
- * and finalise.  exchange != 0 uses the in-kernel peer-memory all-reduce (after physad_xchg_connect), so
+ * run the fused kernel on `slab` (NULL = whole grid), whose last block stores the 16-byte result straight into
+ * mapped pinned host memory (the host polls a sequence number: no copy, no stream synchronisation), and finalise.  exchange != 0 uses the in-kernel peer-memory all-reduce (after physad_xchg_connect), so
  * the returned losses are the GLOBAL ones on every rank; exchange == 0 returns this slab's share
  * (w * local sums / N_global).  This is the call bench.py's `e2e` times. */
 int physad_fused_loss_slab_host(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab,
@@ -279,6 +287,11 @@ int physad_plan_ranges(int tiles, int planes, int slots, int* out, int out_cap);
  * and to the stage-wise physics kernels.  Returns the previous value. */
 int physad_set_exact_residuals(physad_ctx* ctx, int on);
 
+/* Diagnostics: per-block timeline of the following fused launches.  dev_buf (DEVICE memory, zeroed by the caller)
+ * holds blocks_cap x 18 x 2 uint64 {globaltimer ns, SM clock}: slot 0 block start, 1 prologue done, 2+3s / 3+3s /
+ * 4+3s = z-segment s (< 4) start / first halo plane done / end, 14 march done, 15 {SM id, tile-planes owned},
+ * 16 block exit.  NULL switches it off (default).  Used by tools/trace_fused.py. */
+int physad_set_fused_trace(physad_ctx* ctx, unsigned long long* dev_buf, int blocks_cap);
 /* Tuning knob for experiments: selects the fused-kernel variant (0 = default). Returns the previous value. */
 int physad_set_fused_variant(physad_ctx* ctx, int variant);
 /* Number of kernel launches this context has enqueued since creation (bench.py's gpu_launches). */

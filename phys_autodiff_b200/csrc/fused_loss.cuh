@@ -78,38 +78,74 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
 }
 
 // Called by the first warp of one block with this rank's totals; returns the global totals in (a, b)
-// on lane 0.  A peer that never shows up (crashed rank) ends the wait after ~4 s with NaN results
-// instead of hanging the GPU.
-__device__ __forceinline__ void xchg_allreduce2(const XchgArgs& x, double& a, double& b) {
+// on lane 0 and `true` on every lane if all peers arrived.  Lane p owns peer p: it publishes into p's
+// buffer, then ACQUIRES the flag of slot p in its own buffer and reads that slot's payload itself (the
+// release/acquire pair orders exactly those accesses); the `world` pairs are then added in rank order through
+// shuffles, so every rank forms the same sum.
+// Co-residency requirement: the kernels that wait on each other run on DIFFERENT devices (one process per
+// GPU), and every rank must launch the same sequence of exchanging kernels -- a rank that is late only delays
+// the others, a rank that never launches makes them give up after ~4 s: the sums become NaN (so that a consumer
+// who ignores the status cannot use them) and the return value / FusedArgs::status report the timeout.
+__device__ __forceinline__ bool xchg_allreduce2(const XchgArgs& x, double& a, double& b) {
     const int lane = threadIdx.x & 31;
     const int set = int(x.epoch & 1ull) * XCHG_MAX_RANKS;
+    bool ok = true;
+    double pa = 0.0, pb = 0.0;
     if (lane < x.world) {
         XSlot* s = x.peer[lane] + set + x.rank;
         s->a = a;
         s->b = b;
         __threadfence_system();
         st_release_sys(&s->flag, x.epoch);
-    }
-    bool ok = true;
-    if (lane < x.world) {
-        const XSlot* s = x.peer[x.rank] + set + lane;
+        const XSlot* r = x.peer[x.rank] + set + lane;
         const long long t0 = clock64();
-        while (ld_acquire_sys(&s->flag) != x.epoch) {
+        while (ld_acquire_sys(&r->flag) != x.epoch) {
             if (clock64() - t0 > 8000000000ll) { ok = false; break; }
             __nanosleep(64);
         }
+        pa = ld_relaxed_sys(&r->a);
+        pb = ld_relaxed_sys(&r->b);
     }
     ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) {
-        double ta = 0.0, tb = 0.0;
-        for (int p = 0; p < x.world; ++p) {
-            const XSlot* s = x.peer[x.rank] + set + p;
-            ta += ld_relaxed_sys(&s->a);
-            tb += ld_relaxed_sys(&s->b);
-        }
-        a = ok ? ta : __longlong_as_double(0x7ff8000000000000ll);
-        b = ok ? tb : __longlong_as_double(0x7ff8000000000000ll);
+    double ta = 0.0, tb = 0.0;
+    for (int p = 0; p < x.world; ++p) {   // rank order, identical on every rank
+        ta += __shfl_sync(0xffffffffu, pa, p);
+        tb += __shfl_sync(0xffffffffu, pb, p);
     }
+    a = ok ? ta : __longlong_as_double(0x7ff8000000000000ll);
+    b = ok ? tb : __longlong_as_double(0x7ff8000000000000ll);
+    return ok;
+}
+
+// Result record in MAPPED PINNED HOST memory (capi.cu: physad_ctx::h_res): the last block stores the two sums
+// and a status there and then releases `seq` at system scope; the host-buffer entry points poll `seq` instead
+// of enqueueing a 16-byte cudaMemcpyAsync and synchronising the stream (~10 us per step, which is 6 % of a
+// 0.16 ms slab step on 8 GPUs).
+struct HostResult {
+    double a, b;
+    unsigned long long status;   // 0 = ok, 1 = a peer never arrived at the exchange
+    unsigned long long seq;      // written last (st.release.sys)
+};
+
+// Where a reduction's totals go besides acc_out (all optional).
+struct ReduceSink {
+    const XchgArgs* x = nullptr;           // cross-rank exchange before publishing
+    HostResult* host = nullptr;            // mapped host record
+    unsigned long long host_seq = 0;
+    unsigned int* status = nullptr;        // device word, set to 1 when the exchange timed out (sticky)
+};
+
+// Optional per-block timeline (diagnostics, tools/trace_fused.py): TRACE_SLOTS x {globaltimer ns, clock64}.
+constexpr int TRACE_SLOTS = 18;   // 0 start | 1 prologue done | 2+3s,3+3s,4+3s: segment s start / first halo plane done / end | 14 march done | 15 {smid, tile-planes} | 16 block exit
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned int smid() {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
 }
 
 struct FusedArgs {
@@ -129,6 +165,10 @@ struct FusedArgs {
     double* acc_out;         // [2]
     float* R[4];             // slab-local residual outputs or null
     XchgArgs x;              // multi-GPU exchange (world <= 1: off)
+    HostResult* host_res;    // mapped pinned host record or null (the *_host entry points)
+    unsigned long long host_seq;
+    unsigned int* status;    // device word: exchange timeout (sticky) or null
+    unsigned long long* trace;  // [gridDim.x][TRACE_SLOTS][2] or null (diagnostics)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -141,7 +181,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <int NWARPS>
 __device__ __forceinline__ void grid_reduce2_lin(double a, double b, double2* partials, unsigned int* ticket, double* out,
                                                  double2* s_red, unsigned int* s_flag, unsigned int block_lin,
-                                                 unsigned int nblocks, const XchgArgs* x = nullptr) {
+                                                 unsigned int nblocks, const ReduceSink* sink = nullptr) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     a = warp_sum(a);
     b = warp_sum(b);
@@ -173,27 +213,47 @@ __device__ __forceinline__ void grid_reduce2_lin(double a, double b, double2* pa
         double ta = 0.0, tb = 0.0;
 #pragma unroll
         for (int i = 0; i < NWARPS; ++i) { ta += s_red[i].x; tb += s_red[i].y; }
-        if (x != nullptr && x->world > 1) xchg_allreduce2(*x, ta, tb);
+        bool ok = true;
+        if (sink != nullptr && sink->x != nullptr && sink->x->world > 1) ok = xchg_allreduce2(*sink->x, ta, tb);
         if (threadIdx.x == 0) {
             out[0] = ta;
             out[1] = tb;
             *ticket = 0u;
+            if (sink != nullptr) {
+                if (!ok && sink->status) *sink->status = 1u;
+                if (sink->host) {
+                    sink->host->a = ta;
+                    sink->host->b = tb;
+                    sink->host->status = ok ? 0ull : 1ull;
+                    __threadfence_system();
+                    st_release_sys(&sink->host->seq, sink->host_seq);
+                }
+            }
         }
     }
 }
 
 template <int NWARPS>
 __device__ __forceinline__ void grid_reduce2(double a, double b, double2* partials, unsigned int* ticket, double* out,
-                                             double2* s_red, unsigned int* s_flag, const XchgArgs* x = nullptr) {
-    grid_reduce2_lin<NWARPS>(a, b, partials, ticket, out, s_red, s_flag, blockIdx.x, gridDim.x, x);
+                                             double2* s_red, unsigned int* s_flag, const ReduceSink* sink = nullptr) {
+    grid_reduce2_lin<NWARPS>(a, b, partials, ticket, out, s_red, s_flag, blockIdx.x, gridDim.x, sink);
 }
 
 // Exchange-only launch for a rank whose slab is empty (more ranks than planes): it still has to
 // contribute its zeros and must end up with the global sums.
-__global__ void k_xchg_only(const XchgArgs x, double* out) {
+__global__ void k_xchg_only(const __grid_constant__ XchgArgs x, double* out, HostResult* host, unsigned long long host_seq,
+                            unsigned int* status) {
     double a = 0.0, b = 0.0;
-    xchg_allreduce2(x, a, b);
-    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+    const bool ok = xchg_allreduce2(x, a, b);
+    if (threadIdx.x == 0) {
+        out[0] = a; out[1] = b;
+        if (!ok && status) *status = 1u;
+        if (host) {
+            host->a = a; host->b = b; host->status = ok ? 0ull : 1ull;
+            __threadfence_system();
+            st_release_sys(&host->seq, host_seq);
+        }
+    }
 }
 
 // ---- split-phase block barrier (mbarrier): arrive now, wait one plane later ----------------------
@@ -228,6 +288,15 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
     // before it reads plane k-1's neighbours: the ring-duty warps no longer hold the block up.  With four
     // plane buffers a warp can never overwrite data a slower warp still reads (it cannot be two waits ahead).
     __shared__ unsigned long long s_bar[2];
+    // diagnostics: thread 0 stamps slot i of this block's timeline (a null check per segment, nothing per plane)
+    auto stamp = [&](int slot) {
+        if (a.trace != nullptr && threadIdx.x == 0) {
+            unsigned long long* t = a.trace + (size_t(blockIdx.x) * TRACE_SLOTS + slot) * 2;
+            t[0] = globaltimer_ns();
+            t[1] = (unsigned long long)clock64();
+        }
+    };
+    stamp(0);
     if (SPLITBAR) {
         if (threadIdx.x == 0) { mbar_init(&s_bar[0], NWARPS); mbar_init(&s_bar[1], NWARPS); }
         __syncthreads();
@@ -243,6 +312,13 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
     long long wpos = a.ranges[blockIdx.x];
     double acc_s = 0.0, acc_u = 0.0;
     int kbuf = 0;  // running plane-buffer index (keeps rotating across segments)
+    int seg = 0;
+    if (a.trace != nullptr && threadIdx.x == 0) {
+        unsigned long long* t = a.trace + (size_t(blockIdx.x) * TRACE_SLOTS + 15) * 2;
+        t[0] = smid();
+        t[1] = (unsigned long long)(w_end - wpos);
+    }
+    stamp(1);
 
   while (wpos < w_end) {
     const int tile = int(wpos / nzl);
@@ -273,9 +349,13 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
 #pragma unroll
         for (int c = 0; c < 4; ++c) dT[j][c] = real(0);
 
+    if (seg < 4) stamp(2 + 3 * seg);
+    float cz_next = __ldg(a.czs + bc_index(zc0 - 1, a.nz, per));   // one plane ahead: its L2 latency is off the plane's critical path
     for (int k = 0; k <= nplanes + 1; ++k, ++kbuf) {
         const int zk = zc0 - 1 + k;
-        const float cz = __ldg(a.czs + bc_index(zk, a.nz, per));
+        const float cz = cz_next;
+        cz_next = __ldg(a.czs + bc_index(zk + 1, a.nz, per));
+        if (k == 1 && seg < 4) stamp(3 + 3 * seg);
         float* pl = buf + (kbuf & (NB - 1)) * PLANE;
         const bool halo_plane = (k == 0) || (k == nplanes + 1);
         real dTn[P][4];
@@ -372,8 +452,14 @@ k_fused_mlp_phys_loss(const __grid_constant__ MlpConst<H> w, const FusedArgs a) 
     // The next segment starts writing plane buffers that the slowest warp may still be reading
     // (SPLITBAR keeps the one-plane lag across segments, so it needs nothing here).
     if (!SPLITBAR) __syncthreads();
+    if (seg < 4) stamp(4 + 3 * seg);
+    ++seg;
   }
-    grid_reduce2<NWARPS>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag, &a.x);
+    stamp(14);
+    ReduceSink sink;
+    sink.x = &a.x; sink.host = a.host_res; sink.host_seq = a.host_seq; sink.status = a.status;
+    grid_reduce2<NWARPS>(acc_s, acc_u, a.partials, a.ticket, a.acc_out, s_red, &s_flag, &sink);
+    stamp(16);
 }
 
 }  // namespace physad

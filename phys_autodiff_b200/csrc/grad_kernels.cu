@@ -146,11 +146,14 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a,
     constexpr int PPW = 32 / LPP;
     constexpr int NW = GRAD_THREADS / 32;
     constexpr int NGT = GRAD_NACC * HT + 6;   // accumulators | db2[4] | sum R_sigma^2, sum |R_u|^2
-    __shared__ float4 s_x[2][GRAD_THREADS];  // cx, cy, cz, -
-    __shared__ float4 s_gt[2][GRAD_THREADS]; // A_t
-    __shared__ float4 s_gd[2][GRAD_THREADS]; // A_+ (= -A_-)
+    // ONE staging array (the final sums reuse all of it as doubles, so its three parts must be one object):
+    // [0] = cx, cy, cz, -   [1] = A_t   [2] = A_+ (= -A_-), each double-buffered
+    __shared__ float4 s_stage[3][2][GRAD_THREADS];
+    float4 (*s_x)[GRAD_THREADS] = s_stage[0];
+    float4 (*s_gt)[GRAD_THREADS] = s_stage[1];
+    float4 (*s_gd)[GRAD_THREADS] = s_stage[2];
     __shared__ unsigned int s_flag;
-    static_assert(sizeof(float4) * 2 * GRAD_THREADS * 3 >= sizeof(double) * NGT, "final sums reuse the staging arrays");
+    static_assert(sizeof(s_stage) >= sizeof(double) * NGT, "final sums reuse the staging array");
     // double accumulators of every thread, [accumulator][thread] (conflict-free): 40-80 registers per thread saved,
     // which is what lets two blocks per SM stay resident at every width
     extern __shared__ double s_dacc[];
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a,
     // ---- block partial: sum the warps' accumulators through shared memory (reusing the staging arrays) ----
     // partial layout: [k][h] for the GRAD_NACC accumulators (template width), then db2[4]
     __syncthreads();
-    double* s_acc = reinterpret_cast<double*>(&s_x[0][0]);   // NW * 64 doubles per pass: 4 KB of the 8 KB
+    double* s_acc = reinterpret_cast<double*>(&s_stage[0][0][0]);   // NW * 64 doubles per pass: 4 KB of the 24 KB
     double* part = a.partials + size_t(blockIdx.x) * NGT;
 #pragma unroll
     for (int j = 0; j < PPL; ++j)
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_phys_grad(const GradArgs a,
     if (s_flag != gridDim.x - 1) return;
     __threadfence();
     // last block: block-ordered sums, then the gradient in the reference's layouts (runtime width)
-    double* tot = reinterpret_cast<double*>(&s_x[0][0]);
+    double* tot = reinterpret_cast<double*>(&s_stage[0][0][0]);
     for (int e = threadIdx.x; e < NGT; e += GRAD_THREADS) {
         double s = 0.0;
         for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(a.partials + size_t(b) * NGT + e);

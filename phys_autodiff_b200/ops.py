@@ -96,6 +96,21 @@ class Context:
         self._peers = (rank, world)
         return True
 
+    def xchg_status(self) -> bool:
+        """True if an in-kernel exchange since the last call gave up waiting for a peer (synchronises the device)."""
+        v = C.c_int(0)
+        check(self._lib.physad_xchg_status(self._h, C.byref(v)), "xchg_status")
+        return bool(v.value)
+
+    def set_fused_trace(self, buf=None) -> None:
+        """Diagnostics: per-block timeline of the following fused launches into `buf` (a zeroed int64/uint64 CUDA tensor
+        of blocks x 18 x 2 elements, see include/physad_b200.h); None switches it off."""
+        if buf is None:
+            check(self._lib.physad_set_fused_trace(self._h, None, C.c_int(0)), "set_fused_trace")
+        else:
+            check(self._lib.physad_set_fused_trace(self._h, ptr(buf), C.c_int(buf.numel() // 36)), "set_fused_trace")
+        self._trace_keep = buf
+
     def disconnect_peers(self) -> None:
         self._lib.physad_xchg_disconnect(self._h)
         self._peers = None

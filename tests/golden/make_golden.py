@@ -88,6 +88,15 @@ def main():
         r = R.fused_loss(g, w, 0.25, 2e-3, threads=8, want_residuals=True)
         meta["anchors"][f"64c_h{H}"] = dict(loss_sigma=repr(float(r["loss_sigma"])), loss_u=repr(float(r["loss_u"])),
                                             R_sigma0=repr(float(r["R"][0][0])), W1_0=repr(float(w[0][0])))
+    # 3b. the HEADLINE config (BASELINE.json metric: 256^3, seed 777, scale 0.25, t 0.25, dt 2e-3, periodic) and its
+    # width-sweep siblings, whole grid through the unmodified reference on all host threads (~10-30 s each):
+    # pins what bench.py times and what tests/test_gpu_parity.py::test_fused_256_* asserts at 1e-4
+    nthreads = len(os.sched_getaffinity(0))
+    for H in (32, 64, 128):
+        g = Grid(256, 256, 256, 1, 1, 1, 2e-3, True)
+        w = R.mlp_random_init(H, 777, 0.25)
+        r = R.fused_loss(g, w, 0.25, 2e-3, threads=nthreads)
+        meta["anchors"][f"256c_h{H}"] = dict(loss_sigma=repr(float(r["loss_sigma"])), loss_u=repr(float(r["loss_u"])))
     g = Grid(32, 32, 24, 1, 1, 1, 1.0, False)  # test_mlp_grid_infer.cpp:15-20
     w = R.mlp_random_init(64, 123, 0.25)
     y = R.mlp_grid_infer(g, w, 0.3, True)

@@ -20,9 +20,9 @@ def rel_l2(a, b):
 
 
 def bits_equal(a, b):
-    """Value equality of fp32 arrays (+0 == -0; NaN never expected)."""
-    a = np.asarray(a, np.float32); b = np.asarray(b, np.float32)
-    return a.shape == b.shape and bool(np.all(a == b))
+    """BIT equality of fp32 arrays: the uint32 views are compared, so +0 != -0 and NaN payloads count."""
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))
 
 
 def manufactured_fields(g, t, kx=1, ky=1, kz=1, const_u=True):

@@ -105,6 +105,31 @@ def test_gradient_vs_checker(ctx, port, shape, H, per, m1p1, h, dt):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape,H,per,grid_dt,dt", [((40, 24, 13), 64, True, 2e-3, 1e-3), ((33, 18, 7), 32, False, 5e-3, 2e-2)])
+def test_gradient_with_slice_offset_different_from_grid_dt(ctx, port, shape, H, per, grid_dt, dt):
+    """The reference API keeps the slice offset of mlp_generate_fields(t, dt) (src/mlp_grid.cpp:87-89) independent of
+    GridSpec::dt, which alone forms the residual's time derivative (src/phys_cpu.cpp:38).  Loss AND gradient must use
+    1/(2 grid.dt) -- a backward scaled with the call's dt would disagree with the loss it returns."""
+    from phys_autodiff_b200 import MLPConfig, PhysWeights
+    og = OGrid(*shape, 1, 1, 1, grid_dt, per)
+    w = port.mlp_random_init(H, 777, 0.25)
+    want = port.phys_loss_grad(og, w, 0.25, dt, 1.3, 0.7, True, all_double=False)
+    ls, lu, dW1, db1, dW2, db2 = ctx.fused_loss_grad_host(_g(og), MLPConfig(4, H, 4, True), *w, PhysWeights(1.3, 0.7), 0.25, dt)
+    got = np.concatenate([dW1, db1, dW2, db2]).astype(np.float64)
+    gmax = np.abs(want["grad"]).max()
+    assert np.abs(got - want["grad"]).max() <= TOL_GRAD * gmax, (np.abs(got - want["grad"]).max(), gmax)
+    assert abs(ls - want["loss_sigma"]) <= TOL_LOSS * abs(want["loss_sigma"])
+    assert abs(lu - want["loss_u"]) <= TOL_LOSS * abs(want["loss_u"])
+    # the slab form shares grad_args_common
+    from phys_autodiff_b200.ops import slab_for_rank
+    ctx.set_weights(MLPConfig(4, H, 4, True), *w)
+    tot = np.zeros(9 * H + 6)
+    for r in range(3):
+        tot += ctx.fused_loss_grad_slab_acc(_g(og), PhysWeights(1.3, 0.7), 0.25, dt, slab_for_rank(og.nz, r, 3)).cpu().numpy()
+    assert np.abs(tot[2:] - want["grad"]).max() <= TOL_GRAD * gmax
+
+
+@pytest.mark.gpu
 def test_gradient_is_deterministic_and_device_form_agrees(ctx, port):
     from phys_autodiff_b200 import MLPConfig, PhysWeights
     og = OGrid(96, 80, 37, 1, 1, 1, 2e-3, True)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """BASELINE config 5: MLP width/depth sweep at 256^3 (strict fp32, stage-wise: three time slices -> six fields,
-then the physics loss on those fields).  H in {32, 64}, hidden layers L in {1..5}; L = 1 also shows the fused
+then the physics loss on those fields).  H in {32, 64, 128}, hidden layers L in {1..5}; L = 1 also shows the fused
 kernel.  Reports ms, Gpts/s and the fraction of the measured strict FMUL+FADD peak for the ALGORITHMIC flops
 3 * (2*4H + (L-1)*2H^2 + 2*4H) + 3*L*H (ReLU) per point.  Prints JSON."""
 import argparse, json, os, statistics, sys
@@ -13,6 +13,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--hs", default="32,64,128")
+    ap.add_argument("--ls", default="1,2,3,4,5")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -40,9 +42,9 @@ def main():
         return statistics.mean(ts)
 
     out = {"grid": [n, n, n], "strict_fp32_peak_tflops": strict, "rows": []}
-    for H in (32, 64):
+    for H in [int(v) for v in a.hs.split(',')]:
         W1, b1, W2, b2 = ops.mlp_random_init(H, 777, 0.25)
-        for L in (1, 2, 3, 4, 5):
+        for L in [int(v) for v in a.ls.split(',')]:
             Wh = rng.uniform(-0.2, 0.2, (L - 1) * H * H).astype(np.float32)
             bh = rng.uniform(-0.2, 0.2, (L - 1) * H).astype(np.float32)
             ctx.set_weights_deep(MLPConfig(4, H, 4, True), L, W1, b1, Wh, bh, W2, b2)
