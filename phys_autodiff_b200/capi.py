@@ -97,7 +97,8 @@ EXPORTS = [
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libphysad_b200.so")
+    # PHYSAD_LIB: tuning aid (A/B runs of experimental builds of the same sources on one box)
+    return os.environ.get("PHYSAD_LIB") or os.path.join(_HERE, "libphysad_b200.so")
 
 
 def build_library(verbose: bool = False) -> str:
