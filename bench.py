@@ -51,13 +51,26 @@ def ncu_dram_traffic():
         return None
 
 
-def ncu_fma_pipe_active():
-    """sm__pipe_fma_cycles_active (% of active cycles) of the fused kernel from the same committed capture."""
+def golden_losses(H: int, n: int):
+    """Losses the UNMODIFIED reference CPU path gives for this benchmark's inputs on the WHOLE n^3 grid
+    (tests/golden/golden.json, written by tests/golden/make_golden.py in the dev container), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_fused_default_summary.json")) as fh:
-            return float(json.load(fh)[0]["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"][0])
+        with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as fh:
+            a = json.load(fh)["anchors"].get(f"{n}c_h{H}")
+        return (float(a["loss_sigma"]), float(a["loss_u"])) if a else None
     except Exception:
         return None
+
+
+def parity_block(H: int, n: int, ls: float, lu: float):
+    """The timed path's result against the reference's, at the north-star tolerance for the reduced loss."""
+    ref = golden_losses(H, n)
+    if ref is None:
+        return None
+    es, eu = abs(ls - ref[0]) / abs(ref[0]), abs(lu - ref[1]) / abs(ref[1])
+    return {"ref_sigma": ref[0], "ref_u": ref[1], "rel_err_sigma": es, "rel_err_u": eu, "tolerance": 1e-4,
+            "ok": bool(es <= 1e-4 and eu <= 1e-4),
+            "source": f"tests/golden/golden.json anchors[{n}c_h{H}]: unmodified reference CPU path on the whole grid"}
 
 
 def executed_flops_per_point(H: int) -> float:
@@ -177,8 +190,16 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+def workload_name(H: int, n: int) -> str:
+    return (f"fused MLP(4-{H}-4)+phys loss, {n}^3 grid, seed {SEED}, scale {SCALE}, t {T0}, dt {DT}, "
+            f"h 1, periodic, MinusOneToOne (test_mlp_phys_perf.cpp:21-23 at 256^3)")
+
+
 def run_reference_arm(args, rank: int, world: int):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (the reference is
+    single-threaded; its pointwise MLP is driven on all host threads, bit-identical results).  The FIRST timed step
+    runs the WHOLE grid of the workload; the remaining steps a bounded z-sample of it (--ref-planes), so that the
+    default run stays within minutes.  value = points processed / time over all timed steps."""
     if rank != 0:
         return
     H, n = args.hidden, args.grid
@@ -186,21 +207,26 @@ def run_reference_arm(args, rank: int, world: int):
     planes = max(3, min(n, args.ref_planes))
     for _ in range(min(args.warmup, 1)):
         cpu_reference_rate(H, n, planes, threads)
-    times, kind, cores = [], "port", 1
-    for _ in range(args.steps):
+    times, pts, kind, cores, whole_losses = [], 0, "port", 1, None
+    for i in range(args.steps):
+        p = n if i == 0 else planes
         t0 = time.perf_counter()
-        rate, kind, cores, _ = cpu_reference_rate(H, n, planes, threads)
+        rate, kind, cores, losses = cpu_reference_rate(H, n, p, threads)
         times.append(time.perf_counter() - t0)
-    pts = n * n * planes
+        pts += n * n * p
+        if i == 0:
+            whole_losses = losses
     total = sum(times)
-    value = pts * len(times) / total
-    sample = f"{n}x{n}x{planes} planes of the {n}^3 workload per step (same weights, t, dt, periodic), {cores} host threads"
+    value = pts / total
+    sample = (f"step 1: the whole {n}^3 grid ({times[0]:.2f} s); steps 2..{args.steps}: {n}x{n}x{planes} planes of it "
+              f"(same weights, t, dt, periodic); {cores} host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"fused MLP(4-{H}-4)+phys loss, {n}^3 grid, seed {SEED}, dt {DT}, periodic", "hidden": H,
-                   "grid": [n, n, n], "sample": sample},
+        "config": {"workload": workload_name(H, n), "hidden": H, "grid": [n, n, n]},
+        "loss": {"sigma": whole_losses[0], "u": whole_losses[1]},
+        "parity": parity_block(H, n, whole_losses[0], whole_losses[1]),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -385,8 +411,38 @@ def main():
             w2 = ops.mlp_random_init(H2, SEED, SCALE)
             ctx.set_weights(MLPConfig(4, H2, 4, True), *w2)
             t_ms, _, _, _, _ = timed(10, 3)
+            l2s, l2u = ctx.finalize(acc.cpu().numpy(), pw, g.N)
             extra[f"H{H2}"] = {"value": g.N * 10 / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / 10,
-                               "roofline_frac": flops_per_point(H2) * g.N * 10 / (t_ms * 1e-3) / 1e12 / peak_strict}
+                               "roofline_frac": flops_per_point(H2) * g.N * 10 / (t_ms * 1e-3) / 1e12 / peak_strict,
+                               "loss": {"sigma": float(l2s), "u": float(l2u)}, "parity": parity_block(H2, n, float(l2s), float(l2u))}
+        ctx.set_weights(cfg, *w)
+        # BASELINE config 5, depth: 4 -> H -> ... -> H -> 4 with L hidden layers (additive API, parity unpinned for L > 1:
+        # bit-exact against the CPU restatement in the tests), stage-wise: three slices -> six fields (k_mlp_deep), then
+        # the physics loss on them.  frac = algorithmic strict-fp32 flops of the MLP / the measured FMUL+FADD peak.
+        rng = np.random.default_rng(0)
+        sweep = []
+        for H2 in (32, 64, 128):
+            wd = ops.mlp_random_init(H2, SEED, SCALE)
+            for L in (2, 3, 5):
+                Wh = rng.uniform(-0.2, 0.2, (L - 1) * H2 * H2).astype(np.float32)
+                bh = rng.uniform(-0.2, 0.2, (L - 1) * H2).astype(np.float32)
+                ctx.set_weights_deep(MLPConfig(4, H2, 4, True), L, wd[0], wd[1], Wh, bh, wd[2], wd[3])
+                fields = ctx.mlp_generate_fields_deep(g, T0, DT)
+                ts_f, ts_p = [], []
+                for it in range(3):
+                    flush.zero_()
+                    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    e0.record(); ctx.mlp_generate_fields_deep(g, T0, DT); e1.record(); dacc = ctx.phys_loss_acc(g, fields); e2.record()
+                    e2.synchronize()
+                    if it:
+                        ts_f.append(e0.elapsed_time(e1)); ts_p.append(e1.elapsed_time(e2))
+                fl = 3 * (2 * 4 * H2 + (L - 1) * 2 * H2 * H2 + 2 * 4 * H2) + 3 * L * H2
+                ms_f, ms_p = statistics.mean(ts_f), statistics.mean(ts_p)
+                sweep.append({"H": H2, "hidden_layers": L, "ms_fields": ms_f, "ms_phys_loss": ms_p,
+                              "value": g.N / ((ms_f + ms_p) * 1e-3), "unit": UNIT, "mlp_flops_per_point": fl,
+                              "mlp_tflops": fl * g.N / (ms_f * 1e-3) / 1e12, "frac_of_strict_fp32_peak": fl * g.N / (ms_f * 1e-3) / 1e12 / peak_strict})
+                del fields
+        extra["depth_sweep"] = sweep
         ctx.set_weights(cfg, *w)
         # the closed loop (additive): losses + d(L_sigma + L_u)/d(weights) per step, device-resident
         pwc = PhysWeights(1.0, 1.0)
@@ -405,10 +461,23 @@ def main():
             "value": g.N / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms, "kernels_per_step": 4,
             "note": "fields (strict MLP, 3 slices) -> residuals + sums -> stencil adjoint -> MLP backward; median of 10"}
 
+    # N > 1: every rank must hold the same losses, and the in-kernel exchange must agree with a plain NCCL all-reduce
+    multi = None
+    if world > 1:
+        acc2 = ctx.fused_loss_acc(g, T0, DT, slab=slab).clone()
+        dist.all_reduce(acc2, op=dist.ReduceOp.SUM)
+        mine = [float(ls), float(lu)] + [float(v) for v in acc2.cpu().numpy()] + [float(v) for v in acc.cpu().numpy()]
+        allv = [None] * world
+        dist.all_gather_object(allv, mine)
+        same = all(v[:2] == allv[0][:2] for v in allv)
+        rel = max(abs(v[4 + k] - v[2 + k]) / abs(v[2 + k]) for v in allv for k in range(2))
+        multi = {"ranks": world, "same_loss_on_every_rank": bool(same), "in_kernel_exchange_vs_nccl_rel_diff": rel,
+                 "collective": "p2p" if p2p else "nccl", "ok": bool(same and rel <= 1e-12)}
+
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         threads = host_threads()
-        planes = 64 if threads >= 8 else 16
+        planes = (64 if threads >= 8 else 16) if world == 1 else 16   # N > 1: a short sample, the other ranks wait for it
         rate, kind, cores, closs = cpu_reference_rate(H, n, planes, threads)
         rate1, _, _, _ = cpu_reference_rate(H, n, 4, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
@@ -420,8 +489,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"fused MLP(4-{H}-4)+phys loss, {n}^3 grid, seed {SEED}, scale {SCALE}, t {T0}, dt {DT}, "
-                                   f"h 1, periodic, MinusOneToOne (test_mlp_phys_perf.cpp:21-23 at 256^3)",
+            "config": {"workload": workload_name(H, n),
                        "hidden": H, "grid": [n, n, n], "parallelism": f"z-slab x{world}, halo recomputed, 1 all-reduce of 2 doubles "
                                       + ("inside the kernel over NVLink peer memory" if p2p else "(NCCL)" if world > 1 else "(n/a)"),
                        "mode": "strict fp32 MLP (FMUL+FADD, bit-exact); residual arithmetic "
@@ -431,17 +499,18 @@ def main():
                              "between timed steps with a 256 MiB write outside the per-step events",
                        "fused_variant": args.variant},
             "loss": {"sigma": float(ls), "u": float(lu)},
+            "parity": parity_block(H, n, float(ls), float(lu)),
+            "multi_rank_parity": multi,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                     "loss": [float(e2e_out[0]), float(e2e_out[1])]},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32-pipe", "achieved": achieved, "peak": peak_strict, "unit": "TFLOP/s",
-                         "frac": achieved / peak_strict, "traffic": ncu_dram_traffic() if (H == 64 and n == 256 and world == 1) else None,
+                         "frac": achieved / peak_strict, "frac_vs_ffma_peak": achieved / peak_ffma, "traffic": ncu_dram_traffic() if (H == 64 and n == 256 and world == 1) else None,
                          "peak_source": peak_src, "peak_ffma": peak_ffma,
                          "flops_per_point": flops_per_point(H), "kernel_ms_mean": k_mean, "kernel_ms_min": k_min,
                          "executed_flops_per_point": executed_flops_per_point(H),
                          "frac_executed": executed_flops_per_point(H) * slab_pts / (k_mean * 1e-3) / 1e12 / peak_strict,
-                         "fma_pipe_active_pct_ncu": ncu_fma_pipe_active() if (H == 64 and n == 256 and world == 1) else None,
                          "note": "achieved = ALGORITHMIC flops (51H+68)/point x slab points / CUDA-event kernel time; peak = measured "
                                  "non-contracted FMUL+FADD rate (parity mode cannot use FFMA). frac > 1 because the kernel "
                                  "executes fewer operations than the algorithmic count (shared layer-1 prefix across the three "

@@ -19,7 +19,8 @@ void cuda_phys_loss_forward_fused(const GridSpec& g, const PhysWeights& w, const
 // The whole hot path in one kernel: MLP at (x,y,z,t-dt|t|t+dt) over the grid -> residuals -> loss.
 // Equivalent to mlp_generate_fields_cuda followed by cuda_phys_loss_forward_*, without any field
 // ever leaving the chip (the "MLP -> physics mega-kernel" of docs/BENCHMARK_REPORT.md:61).
-// Requires cfg.dims.In == cfg.dims.Out == 4 and H <= 128.
+// Requires cfg.dims.In == cfg.dims.Out == 4 (what the reference's grid driver assumes, src/mlp_grid.cpp:69-80).  H <= 128 runs
+// the fused kernel; wider networks run stage-wise (generic operator per slice, then the stencil + on-device reduction).
 void mlp_phys_loss_fused_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, const PhysWeights& pw,
                               float t, float dt, float* out_loss_sigma, float* out_loss_u, float* opt_R_sigma = nullptr,
                               float* opt_R_ux = nullptr, float* opt_R_uy = nullptr, float* opt_R_uz = nullptr);

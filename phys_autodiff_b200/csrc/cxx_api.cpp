@@ -130,10 +130,42 @@ void mlp_grid_infer_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPW
     mlp_infer_cuda(cfg.dims, w, coords.data(), N, out.data());
 }
 
+// Widths the grid kernels are not instantiated for (H > 128): the reference's own composition (src/mlp_grid.cpp:82-106) --
+// explicit coordinates, the generic operator per time slice, split on the host -- so that the drop-in accepts every
+// H the reference accepts.  In = Out = 4 is what the reference's grid driver itself assumes (its split hard-codes the
+// stride 4, src/mlp_grid.cpp:69-80); other dims are rejected by the C-ABI with PHYSAD_E_UNSUPPORTED.
+static bool grid_kernels_cover(const MLPGridConfig& cfg) { return cfg.dims.In != 4 || cfg.dims.Out != 4 || cfg.dims.H <= 128; }
+
+static void generate_fields_generic(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, float t, float dt,
+                                    std::vector<float>* sig[3], std::vector<float>* vel[3]) {
+    const std::size_t N = std::size_t(g.nx) * g.ny * g.nz;
+    const float ts[3] = {t - dt, t, t + dt};   // src/mlp_grid.cpp:87-89
+    std::vector<float> coords, y(N * 4);
+    for (int s = 0; s < 3; ++s) {
+        make_grid_coords(g, ts[s], cfg.norm, coords);
+        mlp_infer_cuda(cfg.dims, w, coords.data(), N, y.data());
+        sig[s]->resize(N);
+        vel[s]->resize(3 * N);
+        float *ps = sig[s]->data(), *pu = vel[s]->data();
+        for (std::size_t i = 0; i < N; ++i) {   // split_outputs_to_fields, src/mlp_grid.cpp:69-80
+            ps[i] = y[i * 4];
+            pu[i] = y[i * 4 + 1];
+            pu[N + i] = y[i * 4 + 2];
+            pu[2 * N + i] = y[i * 4 + 3];
+        }
+    }
+}
+
 void mlp_generate_fields_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, float t, float dt,
                               std::vector<float>& sigma_tm1, std::vector<float>& sigma_t, std::vector<float>& sigma_tp1,
                               std::vector<float>& u_tm1, std::vector<float>& u_t, std::vector<float>& u_tp1) {
     const std::size_t N = std::size_t(g.nx) * g.ny * g.nz;
+    if (!grid_kernels_cover(cfg)) {
+        std::vector<float>* sig[3] = {&sigma_tm1, &sigma_t, &sigma_tp1};
+        std::vector<float>* vel[3] = {&u_tm1, &u_t, &u_tp1};
+        generate_fields_generic(g, cfg, w, t, dt, sig, vel);
+        return;
+    }
     for (auto* s : {&sigma_tm1, &sigma_t, &sigma_tp1}) s->resize(N);
     for (auto* u : {&u_tm1, &u_t, &u_tp1}) u->resize(3 * N);
     std::lock_guard<std::mutex> lk(g_mu);
@@ -220,6 +252,15 @@ void cuda_phys_loss_backward_fused(const GridSpec& g, const PhysWeights& w, cons
 void mlp_phys_loss_fused_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, const PhysWeights& pw,
                               float t, float dt, float* out_loss_sigma, float* out_loss_u, float* opt_R_sigma,
                               float* opt_R_ux, float* opt_R_uy, float* opt_R_uz) {
+    if (!grid_kernels_cover(cfg)) {   // H > 128: stage-wise (fields through the generic operator, then the stencil + reduction)
+        std::vector<float> s[3], u[3];
+        std::vector<float>* sig[3] = {&s[0], &s[1], &s[2]};
+        std::vector<float>* vel[3] = {&u[0], &u[1], &u[2]};
+        generate_fields_generic(g, cfg, w, t, dt, sig, vel);
+        cuda_phys_loss_forward_fused(g, pw, s[0].data(), s[1].data(), s[2].data(), u[0].data(), u[1].data(), u[2].data(),
+                                     out_loss_sigma, out_loss_u, opt_R_sigma, opt_R_ux, opt_R_uy, opt_R_uz);
+        return;
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     const physad_grid cg = to_c(g);
     const physad_phys_weights cw = to_c(pw);

@@ -37,6 +37,18 @@ def test_reference_parity_program(name):
     assert "FAIL" not in r.stdout.upper().replace("[PASS]", ""), r.stdout[-2000:]
 
 
+@pytest.mark.parametrize("name", ["test_mlp_grid_infer", "test_mlp_phys_integration_inputs", "test_phys_cuda_nonfused_vs_cpu",
+                                  "test_phys_cuda_fused_vs_nonfused", "test_phys_cpu_ref"])
+def test_reference_parity_program_compiled_against_this_repos_headers(name):
+    """The same unmodified test sources compiled with -I<this repo>/include instead of the reference's headers (their CPU
+    half still comes from the reference's objects, built with the reference's headers): the two header sets must describe
+    one ABI -- struct layouts and defaults (GridSpec{periodic = true}, MLPDims{4, 64, 4}, PhysWeights{1, 1}), default
+    arguments (mlp_random_init seed/scale, nullable opt_R_*), signatures."""
+    r = _run("ownhdr_" + name)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "FAIL" not in r.stdout.upper().replace("[PASS]", ""), r.stdout[-2000:]
+
+
 @pytest.mark.parametrize("name", ["test_phys_perf", "test_mlp_phys_perf"])
 def test_reference_benchmark_program_runs(name):
     """The reference's CSV timing harnesses (docs/BENCHMARK_REPORT.md shapes) through the host-pointer API."""
@@ -53,6 +65,14 @@ def test_reference_mlp_compare_reports_zero_difference():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     diffs = [float(v) for v in re.findall(r"(?:diff|err)[^=:\n]*[=:]\s*([0-9.eE+-]+)", r.stdout)]
     assert diffs and all(d == 0.0 for d in diffs), r.stdout[-2000:]
+
+
+def test_wide_mlp_through_the_reference_names():
+    """tests/refprogs/wide_mlp_dropin.cpp (ours): H = 192 and 130 -- widths the grid kernels are not built for -- through
+    phys::mlp_generate_fields_cuda / mlp_grid_infer_cuda / mlp_phys_loss_fused_cuda against the reference's CPU objects."""
+    r = _run("wide_mlp_dropin")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "[PASS]" in r.stdout and "[FAIL]" not in r.stdout
 
 
 def test_closed_loop_program_through_the_cxx_api():
