@@ -3,6 +3,7 @@
 // decides shapes, fills the kernel-parameter weight block and moves bytes.
 #include "../../include/physad_b200.h"
 #include "deep_kernels.cuh"
+#include "dense_kernels.cuh"
 #include "grad_kernels.cuh"
 #include "stage_kernels.cuh"
 
@@ -703,6 +704,26 @@ int physad_set_weights(physad_ctx* c, const physad_mlp_config* cfg, const float*
 }
 
 
+namespace {
+// a1[i,h] = relu(b1[h] + sum_k W1[h,k] x[i,k])          (src/mlp_cpu.cpp:18-24)
+GemmArgs gemm_hidden(const physad_ctx* c, const float* x, float* act, size_t B) {
+    GemmArgs g{};
+    const int In = c->cfg.In, H = c->cfg.H;
+    g.A = x; g.a_ms = In; g.a_ks = 1; g.B = c->dW1; g.b_ks = 1; g.b_ns = In; g.ones_col = -1; g.init = c->db1;
+    g.M = int(B); g.N = H; g.K = In; g.epilogue = GEMM_RELU; g.C = act; g.c_ms = H; g.n_split = H;
+    return g;
+}
+// y[i,o] = b2[o] + sum_h W2[o,h] a1[i,h]   (src/mlp_cpu.cpp:27-34), or gz2 = scale * (y - target) when target != null (:58)
+GemmArgs gemm_out(const physad_ctx* c, const float* act, float* out, size_t B, const float* target, float scale) {
+    GemmArgs g{};
+    const int H = c->cfg.H, Out = c->cfg.Out;
+    g.A = act; g.a_ms = H; g.a_ks = 1; g.B = c->dW2; g.b_ks = 1; g.b_ns = H; g.ones_col = -1; g.init = c->db2;
+    g.M = int(B); g.N = Out; g.K = H; g.epilogue = target ? GEMM_SCALED_DIFF : GEMM_STORE; g.aux = target; g.scale = scale;
+    g.C = out; g.c_ms = Out; g.n_split = Out;
+    return g;
+}
+}  // namespace
+
 // ---- MLP operator -----------------------------------------------------------------------------
 int physad_mlp_forward_dev(physad_ctx* c, const float* x, float* y, size_t B, void* stream) {
     if (!c || (B && (!x || !y))) return fail(PHYSAD_E_INVALID, "mlp_forward: null argument");
@@ -720,10 +741,11 @@ int physad_mlp_forward_dev(physad_ctx* c, const float* x, float* y, size_t B, vo
             reinterpret_cast<const float4*>(x), c->dW1, c->db1, c->dW2, c->db2, reinterpret_cast<float4*>(y), B, H);
         c->launches++;
     } else {
+        if (B > size_t(65535) * 64) return fail(PHYSAD_E_UNSUPPORTED, "mlp_forward: more than 4 194 240 rows per call for generic dims");
         float* act = nullptr;
         CU(cudaMallocAsync(&act, B * size_t(H) * sizeof(float), st));
-        k_mlp_generic_hidden<<<unsigned((B * size_t(H) + 255) / 256), 256, 0, st>>>(x, c->dW1, c->db1, act, B, In, H);
-        k_mlp_generic_out<<<unsigned((B * size_t(Out) + 255) / 256), 256, 0, st>>>(act, c->dW2, c->db2, y, B, H, Out);
+        CU(cudaError_t(strict_gemm_launch(gemm_hidden(c, x, act, B), st)));
+        CU(cudaError_t(strict_gemm_launch(gemm_out(c, act, y, B, nullptr, 0.f), st)));
         c->launches += 2;
         CU(cudaFreeAsync(act, st));
     }
@@ -761,17 +783,26 @@ int physad_mlp_backward_dev(physad_ctx* c, const float* x, const float* y_target
     CU(cudaMallocAsync(&act, B * size_t(H) * sizeof(float), st));
     CU(cudaMallocAsync(&gz1, B * size_t(H) * sizeof(float), st));
     CU(cudaMallocAsync(&gz2, B * size_t(Out) * sizeof(float), st));
-    auto nb = [](size_t n) { return unsigned((n + 255) / 256); };
+    if (B > size_t(65535) * 64) return fail(PHYSAD_E_UNSUPPORTED, "mlp_backward: more than 4 194 240 rows per call");
     const float scale = 2.f / float(B * size_t(Out));  // src/mlp_cpu.cpp:58
-    k_mlp_generic_hidden<<<nb(B * H), 256, 0, st>>>(x, c->dW1, c->db1, act, B, In, H);
-    k_bwd_gz2<<<nb(B * Out), 256, 0, st>>>(act, c->dW2, c->db2, y_target, gz2, B, H, Out, scale);
-    k_bwd_dW<<<nb(size_t(Out) * H), 256, 0, st>>>(gz2, act, dW2, B, Out, H);
-    k_bwd_db<<<nb(Out), 256, 0, st>>>(gz2, db2, B, Out);
-    k_bwd_gz1<<<nb(B * H), 256, 0, st>>>(gz2, c->dW2, act, gz1, B, H, Out);
-    k_bwd_dW<<<nb(size_t(H) * In), 256, 0, st>>>(gz1, x, dW1, B, H, In);
-    k_bwd_db<<<nb(H), 256, 0, st>>>(gz1, db1, B, H);
-    c->launches += 7;
-    CU(cudaGetLastError());
+    // five strict contractions (dense_kernels.cuh); every gradient entry is the reference's sequential fp32 sum over the
+    // batch, i ascending -- which is also why the batch cannot be split over blocks: partial sums would round differently
+    GemmArgs gz1g{}, dw2{}, dw1{};
+    // gz1[i,h] = (sum_o gz2[i,o] W2[o,h]) * (a1[i,h] > 0)
+    gz1g.A = gz2; gz1g.a_ms = Out; gz1g.a_ks = 1; gz1g.B = c->dW2; gz1g.b_ks = H; gz1g.b_ns = 1; gz1g.ones_col = -1;
+    gz1g.M = int(B); gz1g.N = H; gz1g.K = Out; gz1g.epilogue = GEMM_MASK; gz1g.aux = act; gz1g.C = gz1; gz1g.c_ms = H; gz1g.n_split = H;
+    // dW2[o,h] = sum_i gz2[i,o] a1[i,h],  db2[o] = sum_i gz2[i,o]  (the extra all-ones column: g * 1 is exact)
+    dw2.A = gz2; dw2.a_ms = 1; dw2.a_ks = Out; dw2.B = act; dw2.b_ks = H; dw2.b_ns = 1; dw2.ones_col = H;
+    dw2.M = Out; dw2.N = H + 1; dw2.K = int(B); dw2.epilogue = GEMM_STORE; dw2.C = dW2; dw2.c_ms = H; dw2.n_split = H; dw2.C2 = db2;
+    // dW1[h,k] = sum_i gz1[i,h] x[i,k],  db1[h] = sum_i gz1[i,h]
+    dw1.A = gz1; dw1.a_ms = 1; dw1.a_ks = H; dw1.B = x; dw1.b_ks = In; dw1.b_ns = 1; dw1.ones_col = In;
+    dw1.M = H; dw1.N = In + 1; dw1.K = int(B); dw1.epilogue = GEMM_STORE; dw1.C = dW1; dw1.c_ms = In; dw1.n_split = In; dw1.C2 = db1;
+    CU(cudaError_t(strict_gemm_launch(gemm_hidden(c, x, act, B), st)));
+    CU(cudaError_t(strict_gemm_launch(gemm_out(c, act, gz2, B, y_target, scale), st)));
+    CU(cudaError_t(strict_gemm_launch(dw2, st)));
+    CU(cudaError_t(strict_gemm_launch(gz1g, st)));
+    CU(cudaError_t(strict_gemm_launch(dw1, st)));
+    c->launches += 5;
     CU(cudaFreeAsync(act, st));
     CU(cudaFreeAsync(gz1, st));
     CU(cudaFreeAsync(gz2, st));

@@ -73,10 +73,9 @@ __global__ void __launch_bounds__(256) k_mlp_grid(const __grid_constant__ MlpCon
 }
 
 // ---------------------------------------------------------------------------------------------
-// MLP on an explicit coordinate/feature array, generic In/H/Out (mlp_forward<ExecCuda>,
-// include/mlp.h:5-6).  Weights are staged once per block in shared memory in their reference
-// layouts.  In = Out = 4 takes the register path; anything else goes through the two generic
-// kernels with a [B x H] activation scratch, like the reference's own layout (src/mlp_cpu.cpp:16).
+// MLP on an explicit coordinate/feature array (mlp_forward<ExecCuda>, include/mlp.h:5-6), In = Out = 4: weights
+// staged once per block in shared memory in their reference layouts, one point per thread.  Any other In / Out, and
+// the MSE backward (mlp_backward<ExecCuda>), go through the strict register-tiled contraction of dense_kernels.cuh.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_mlp_forward_4x4(const float4* __restrict__ x, const float* __restrict__ W1,
                                                          const float* __restrict__ b1, const float* __restrict__ W2,
@@ -111,84 +110,6 @@ __global__ void __launch_bounds__(256) k_mlp_forward_4x4(const float4* __restric
         o3 = __fadd_rn(o3, __fmul_rn(d, act));
     }
     y[i] = make_float4(o0, o1, o2, o3);
-}
-
-__global__ void __launch_bounds__(256) k_mlp_generic_hidden(const float* __restrict__ x, const float* __restrict__ W1,
-                                                            const float* __restrict__ b1, float* __restrict__ act,
-                                                            size_t B, int In, int H) {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= B * size_t(H)) return;
-    const size_t i = e / H;
-    const int h = int(e % H);
-    float s = b1[h];
-    for (int k = 0; k < In; ++k) s = __fadd_rn(s, __fmul_rn(W1[size_t(h) * In + k], x[i * In + k]));
-    act[e] = relu_ref(s);
-}
-
-__global__ void __launch_bounds__(256) k_mlp_generic_out(const float* __restrict__ act, const float* __restrict__ W2,
-                                                         const float* __restrict__ b2, float* __restrict__ y, size_t B,
-                                                         int H, int Out) {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= B * size_t(Out)) return;
-    const size_t i = e / Out;
-    const int o = int(e % Out);
-    float s = b2[o];
-    for (int h = 0; h < H; ++h) s = __fadd_rn(s, __fmul_rn(W2[size_t(o) * H + h], act[i * H + h]));
-    y[e] = s;
-}
-
-// ---------------------------------------------------------------------------------------------
-// MLP backward (MSE weight gradients), reference src/mlp_cpu.cpp:38-85 / include/mlp.h:8-9.
-// not on the grid->loss path, provided so the whole operator API of the
-// reference is real.  The reference accumulates every gradient entry SEQUENTIALLY over the batch in
-// fp32 (`dW2[o,h] += gz2[i,o]*a1[i,h]`, i ascending, separate multiply and add), so bit-exactness
-// fixes the algorithm: one thread per gradient entry walks the batch in order with __fmul_rn/__fadd_rn.
-// (Its own CUDA kernels have the same shape, src/mlp_cuda.cu:45-89, but contract to FFMA.)
-//   k_bwd_gz2 : gz2[i,o] = (2/float(B*Out)) * (y[i,o] - target[i,o]),  y from the activations
-//   k_bwd_gz1 : gz1[i,h] = (sum_o gz2[i,o]*W2[o,h]) * (a1[i,h] > 0)     (relu'(z1) == (a1 > 0))
-//   k_bwd_dW  : dW[r,c]  = sum_i G[i,r] * A[i,c]   (dW2: G=gz2, A=a1;  dW1: G=gz1, A=x)
-//   k_bwd_db  : db[r]    = sum_i G[i,r]
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bwd_gz2(const float* __restrict__ act, const float* __restrict__ W2,
-                                                 const float* __restrict__ b2, const float* __restrict__ target,
-                                                 float* __restrict__ gz2, size_t B, int H, int Out, float scale) {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= B * size_t(Out)) return;
-    const size_t i = e / Out;
-    const int o = int(e % Out);
-    float s = b2[o];
-    for (int h = 0; h < H; ++h) s = __fadd_rn(s, __fmul_rn(W2[size_t(o) * H + h], act[i * H + h]));
-    gz2[e] = __fmul_rn(scale, __fsub_rn(s, target[e]));
-}
-
-__global__ void __launch_bounds__(256) k_bwd_gz1(const float* __restrict__ gz2, const float* __restrict__ W2,
-                                                 const float* __restrict__ act, float* __restrict__ gz1, size_t B, int H,
-                                                 int Out) {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= B * size_t(H)) return;
-    const size_t i = e / H;
-    const int h = int(e % H);
-    float s = 0.f;
-    for (int o = 0; o < Out; ++o) s = __fadd_rn(s, __fmul_rn(gz2[i * Out + o], W2[size_t(o) * H + h]));
-    gz1[e] = __fmul_rn(s, act[e] > 0.f ? 1.f : 0.f);
-}
-
-__global__ void __launch_bounds__(256) k_bwd_dW(const float* __restrict__ G, const float* __restrict__ A,
-                                                float* __restrict__ dW, size_t B, int R, int Cn) {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= size_t(R) * Cn) return;
-    const int r = int(e / Cn), c = int(e % Cn);
-    float s = 0.f;
-    for (size_t i = 0; i < B; ++i) s = __fadd_rn(s, __fmul_rn(G[i * R + r], A[i * Cn + c]));
-    dW[e] = s;
-}
-
-__global__ void __launch_bounds__(256) k_bwd_db(const float* __restrict__ G, float* __restrict__ db, size_t B, int R) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    float s = 0.f;
-    for (size_t i = 0; i < B; ++i) s = __fadd_rn(s, G[i * R + r]);
-    db[r] = s;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -133,8 +133,9 @@ def test_strict_kernels_have_no_contracted_fma_in_mlp(libpath):
     assert len(gradk) == 3 and all(v["FMUL2"] >= 5 and v["FADD2"] >= 6 and v["FFMA2"] > 0 for v in gradk.values()), gradk
     fused = {k: v for k, v in counts.items() if "k_fused_mlp_phys_loss" in k}
     assert fused and all(v["FMUL"] + v.get("FMUL2", 0) > 0 for v in fused.values())
-    grid = {k: v for k, v in counts.items() if "k_mlp_grid" in k or "k_mlp_forward_4x4" in k or "k_mlp_generic" in k}
-    assert grid, "MLP kernels not found in SASS"
+    grid = {k: v for k, v in counts.items() if "k_mlp_grid" in k or "k_mlp_forward_4x4" in k or "k_strict_gemm" in k
+            or "k_mlp_deep" in k}
+    assert grid and any("k_strict_gemm" in k for k in grid) and any("k_mlp_deep" in k for k in grid), "MLP kernels not found in SASS"
     for k, v in grid.items():
         assert v["FMUL"] + v["FMUL2"] > 0 and v["FADD"] + v["FADD2"] > 0, (k, v)
         assert v["FADD2"] >= v["FMUL2"], (k, v)  # every packed product is followed by its own packed add
