@@ -464,6 +464,8 @@ def main():
     # N > 1: every rank must hold the same losses, and the in-kernel exchange must agree with a plain NCCL all-reduce
     multi = None
     if world > 1:
+        step()                                   # acc <- the global sums through the timed path (kernel_only() left the slab's there)
+        barrier()
         acc2 = ctx.fused_loss_acc(g, T0, DT, slab=slab).clone()
         dist.all_reduce(acc2, op=dist.ReduceOp.SUM)
         mine = [float(ls), float(lu)] + [float(v) for v in acc2.cpu().numpy()] + [float(v) for v in acc.cpu().numpy()]

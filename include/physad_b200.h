@@ -292,6 +292,14 @@ int physad_set_exact_residuals(physad_ctx* ctx, int on);
  * 4+3s = z-segment s (< 4) start / first halo plane done / end, 14 march done, 15 {SM id, tile-planes owned},
  * 16 block exit.  NULL switches it off (default).  Used by tools/trace_fused.py. */
 int physad_set_fused_trace(physad_ctx* ctx, unsigned long long* dev_buf, int blocks_cap);
+/* Advection scheme of the STAGE-WISE physics operators (phys_residuals / phys_loss / phys_backward_from_fields, *_dev
+ * and *_host).  0 (default): central differences, the reference (src/phys_cpu.cpp:80-93).  1: first-order UPWIND for the
+ * advective derivatives of u . grad(f) -- (f - f_minus)/h where u_j > 0, (f_plus - f)/h otherwise; divergence and time
+ * derivative stay central.  ADDITIVE: the reference plans this switch (REQUIREMENT.md:123-134: "consistent with the central
+ * scheme for small velocities, no NaN on large random velocity fields") and never ships it, so parity is against
+ * oracle/oracle.c's restatement only ("unpinned").  The fused kernel and the closed-loop gradient implement the central
+ * scheme only and return PHYSAD_E_UNSUPPORTED while upwind is selected.  Returns the previous value (-1: bad argument). */
+int physad_set_advection(physad_ctx* ctx, int scheme);
 /* Tuning knob for experiments: selects the fused-kernel variant (0 = default). Returns the previous value. */
 int physad_set_fused_variant(physad_ctx* ctx, int variant);
 /* Number of kernel launches this context has enqueued since creation (bench.py's gpu_launches). */

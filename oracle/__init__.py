@@ -152,6 +152,14 @@ class _Oracle:
 class PortOracle(_Oracle):
     kind = "port"
 
+    def phys_residuals_upwind(self, g: Grid, fields):
+        """First-order upwind advection (additive switch, parity unpinned: oracle.c is the only statement of it)."""
+        N = g.N
+        R = [np.empty(N, np.float32) for _ in range(4)]
+        f = self.lib.oracle_phys_residuals_upwind; f.restype = None
+        f(C.byref(g.c()), *[_fp(a) for a in fields], *[_fp(r) for r in R])
+        return tuple(R)
+
     def fused_loss(self, g: Grid, w, t, dt, w_sigma=1.0, w_u=1.0, m1p1=True, want_residuals=False):
         """Whole path on one thread -> dict(loss_sigma, loss_u, acc_sigma, acc_u[, R])."""
         W1, b1, W2, b2 = w

@@ -336,6 +336,48 @@ void oracle_phys_residuals(const oracle_grid* g, const float* s_m, const float* 
 #undef LIN
 }
 
+/* First-order UPWIND advection (the "upwind switch" the reference plans and never ships, REQUIREMENT.md:123-134 --
+ * PARITY UNPINNED: there is no reference implementation; this restatement is the checker).  Everything is as in
+ * oracle_phys_residuals (src/phys_cpu.cpp:66-109: float loads widened to double, central time difference, the
+ * divergence in sigma * div(u) by central differences) except the advective derivatives of u . grad(f):
+ *     d f / d x_j  ->  (f(x) - f(x - e_j)) / h_j   if u_j(x) > 0,   (f(x + e_j) - f(x)) / h_j   otherwise
+ * with the same wrap / clamp neighbour rule (a clamped neighbour is the point itself: the one-sided difference is 0). */
+void oracle_phys_residuals_upwind(const oracle_grid* g, const float* s_m, const float* s_0, const float* s_p, const float* u_m,
+                                  const float* u_0, const float* u_p, float* Rs, float* Rx, float* Ry, float* Rz) {
+    const int nx = g->nx, ny = g->ny, nz = g->nz, per = g->periodic;
+    const size_t N = (size_t)nx * ny * nz;
+    const double i2t = 1.0 / (2.0 * (double)g->dt);
+    const double i2[3] = {1.0 / (2.0 * (double)g->hx), 1.0 / (2.0 * (double)g->hy), 1.0 / (2.0 * (double)g->hz)};
+    const double i1[3] = {1.0 / (double)g->hx, 1.0 / (double)g->hy, 1.0 / (double)g->hz};
+#define LIN(X, Y, Z) ((size_t)(((Z) * ny + (Y)) * nx + (X)))
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                const size_t i = LIN(x, y, z);
+                const size_t ip[3] = {LIN(nb(x + 1, nx, per), y, z), LIN(x, nb(y + 1, ny, per), z), LIN(x, y, nb(z + 1, nz, per))};
+                const size_t im[3] = {LIN(nb(x - 1, nx, per), y, z), LIN(x, nb(y - 1, ny, per), z), LIN(x, y, nb(z - 1, nz, per))};
+                const float* f[4] = {s_0, u_0, u_0 + N, u_0 + 2 * N};
+                const float* fp[4] = {s_p, u_p, u_p + N, u_p + 2 * N};
+                const float* fm[4] = {s_m, u_m, u_m + N, u_m + 2 * N};
+                const double u[3] = {(double)u_0[i], (double)u_0[N + i], (double)u_0[2 * N + i]};
+                double div = 0.0;
+                for (int d = 0; d < 3; ++d) div += ((double)f[1 + d][ip[d]] - (double)f[1 + d][im[d]]) * i2[d];
+                float* R[4] = {Rs, Rx, Ry, Rz};
+                for (int c = 0; c < 4; ++c) {
+                    double adv = 0.0;
+                    for (int d = 0; d < 3; ++d) {
+                        const double back = ((double)f[c][i] - (double)f[c][im[d]]) * i1[d];
+                        const double fwd = ((double)f[c][ip[d]] - (double)f[c][i]) * i1[d];
+                        adv += u[d] * (u[d] > 0.0 ? back : fwd);
+                    }
+                    double r = ((double)fp[c][i] - (double)fm[c][i]) * i2t + adv;
+                    if (c == 0) r += (double)s_0[i] * div;
+                    R[c][i] = (float)r;
+                }
+            }
+#undef LIN
+}
+
 /* Sum of squares over a point range, sequential in double as src/phys_cpu.cpp:140-145. */
 void oracle_sumsq(const float* Rs, const float* Rx, const float* Ry, const float* Rz, size_t i0, size_t i1, double* acc_s,
                   double* acc_u) {

@@ -72,6 +72,7 @@ struct physad_ctx {
     uint64_t launches = 0;
     int fused_variant = 0;
     int exact_residuals = 0;  // 1: residual arithmetic in double exactly as the CPU reference; 0: fp32 with FMAs
+    int advection = 0;        // 0: central differences (the reference); 1: first-order upwind advection (additive switch)
     // deeper MLPs (physad_set_weights_deep): hidden->hidden layers in the kernel's layout
     int deep_layers = 0;          // L (0 = not set)
     float *d_wh = nullptr, *d_bh = nullptr;
@@ -374,6 +375,9 @@ int launch_fused_h(physad_ctx* c, const physad_grid* g, const physad_slab& s, co
 
 int launch_fused(physad_ctx* c, const physad_grid* g, const physad_slab& s, float t, float dt, double* acc,
                  float* const R[4], cudaStream_t st, bool xchg = false) {
+    if (c->advection != 0)
+        return fail(PHYSAD_E_UNSUPPORTED, "fused_loss: the fused kernel implements the reference's central scheme only; "
+                                          "upwind advection runs stage-wise (generate_fields + phys_loss)");
     if (xchg && (c->xworld <= 1 || !c->xbuf))
         return fail(PHYSAD_E_INVALID, "fused_loss_allreduce: call physad_xchg_connect first");
     if (s.z_end == s.z_begin) {  // empty slab: the sum over nothing (still takes part in the exchange)
@@ -444,9 +448,12 @@ int launch_phys(physad_ctx* c, const physad_grid* g_in, PhysArgs a, cudaStream_t
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.periodic = g->periodic != 0;
     a.inv2dt = inv2(g->dt); a.inv2hx = inv2(g->hx); a.inv2hy = inv2(g->hy); a.inv2hz = inv2(g->hz);
     a.inv2dt_d = inv2d(g->dt); a.inv2hx_d = inv2d(g->hx); a.inv2hy_d = inv2d(g->hy); a.inv2hz_d = inv2d(g->hz);
-    // 128-bit form when rows are quad-aligned and wide enough to fill the 64-quad blocks reasonably
+    a.inv1hx_d = 1.0 / double(g->hx); a.inv1hy_d = 1.0 / double(g->hy); a.inv1hz_d = 1.0 / double(g->hz);
+    a.inv1hx = float(a.inv1hx_d); a.inv1hy = float(a.inv1hy_d); a.inv1hz = float(a.inv1hz_d);
+    const bool upwind = c->advection == 1;
+    // 128-bit form when rows are quad-aligned and wide enough to fill the 64-quad blocks reasonably (central scheme only)
     static const bool no_v4 = getenv("PHYSAD_NO_V4") != nullptr;  // tuning aid
-    bool v4 = !no_v4 && g->nx % 4 == 0 && g->nx >= 128;
+    bool v4 = !upwind && !no_v4 && g->nx % 4 == 0 && g->nx >= 128;
     const void* ptrs[12] = {a.s_m, a.s_0, a.s_p, a.u_m, a.u_0, a.u_p, a.R[0], a.R[1], a.R[2], a.R[3], a.halo_lo, a.halo_hi};
     for (const void* p : ptrs) v4 = v4 && (uintptr_t(p) % 16 == 0);
     v4 = v4 && (size_t(g->nx) * g->ny * g->nz) % 4 == 0;  // channel stride of the u arrays
@@ -482,7 +489,10 @@ int launch_phys(physad_ctx* c, const physad_grid* g_in, PhysArgs a, cudaStream_t
         if (int rc = ensure_partials(c, size_t(tx) * ty * nch)) return rc;
         a.partials = c->partials; a.ticket = c->ticket;
     }
-    if (c->exact_residuals) k_phys_residual<WRITE_R, REDUCE, SCALE, true><<<grid, 256, 0, st>>>(a);
+    if (upwind) {
+        if (c->exact_residuals) k_phys_residual<WRITE_R, REDUCE, SCALE, true, true><<<grid, 256, 0, st>>>(a);
+        else k_phys_residual<WRITE_R, REDUCE, SCALE, false, true><<<grid, 256, 0, st>>>(a);
+    } else if (c->exact_residuals) k_phys_residual<WRITE_R, REDUCE, SCALE, true><<<grid, 256, 0, st>>>(a);
     else k_phys_residual<WRITE_R, REDUCE, SCALE, false><<<grid, 256, 0, st>>>(a);
     c->launches++;
     CU(cudaGetLastError());
@@ -675,6 +685,12 @@ int physad_set_exact_residuals(physad_ctx* c, int on) {
     if (!c) return -1;
     const int prev = c->exact_residuals;
     c->exact_residuals = on ? 1 : 0;
+    return prev;
+}
+int physad_set_advection(physad_ctx* c, int scheme) {
+    if (!c || (scheme != 0 && scheme != 1)) return -1;
+    const int prev = c->advection;
+    c->advection = scheme;
     return prev;
 }
 int physad_set_fused_variant(physad_ctx* c, int v) {
@@ -1253,6 +1269,7 @@ int physad_fused_loss_grad_dev(physad_ctx* c, const physad_grid* g, const physad
     if (!c || !w || !acc || !grad) return fail(PHYSAD_E_INVALID, "fused_loss_grad: null argument");
     if (int rc = check_grid(g)) return rc;
     if (int rc = need_4x4(c, "fused_loss_grad")) return rc;
+    if (c->advection != 0) return fail(PHYSAD_E_UNSUPPORTED, "fused_loss_grad: the stencil adjoint is that of the central scheme");
     DeviceGuard dg(c->device);
     cudaStream_t st = cudaStream_t(stream);
     const size_t N = size_t(g->nx) * g->ny * g->nz;
@@ -1285,6 +1302,7 @@ int physad_fused_loss_grad_slab_dev(physad_ctx* c, const physad_grid* g, const p
     DeviceGuard dg(c->device);
     cudaStream_t st = cudaStream_t(stream);
     const int H = c->cfg.H;
+    if (c->advection != 0) return fail(PHYSAD_E_UNSUPPORTED, "fused_loss_grad_slab: the stencil adjoint is that of the central scheme");
     if (s.z_begin == s.z_end) {
         CU(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
         CU(cudaMemsetAsync(grad, 0, size_t(9 * H + 4) * sizeof(double), st));

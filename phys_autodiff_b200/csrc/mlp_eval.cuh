@@ -231,4 +231,25 @@ __device__ __forceinline__ void point_residual(const float (&f)[4], const double
     }
 }
 
+// First-order UPWIND advection (additive switch; the reference plans it, REQUIREMENT.md:123-134, and never ships it:
+// parity is against oracle.c's oracle_phys_residuals_upwind only).  As point_residual, except that the advective
+// derivative of f_c along axis j is one-sided against the velocity: (f - f_minus)/h if u_j > 0, (f_plus - f)/h otherwise;
+// the divergence in sigma * div(u) and the time derivative stay central.  T = float (default) or double (exact mode).
+template <typename T>
+__device__ __forceinline__ void point_residual_upwind(const float (&f)[4], const float (&xm)[4], const float (&xp)[4],
+                                                      const float (&ym)[4], const float (&yp)[4], const float (&zm)[4],
+                                                      const float (&zp)[4], const T (&dT)[4], T i1x, T i1y, T i1z, T i2x, T i2y,
+                                                      T i2z, float (&R)[4]) {
+    const T div = ((T(xp[1]) - T(xm[1])) * i2x + (T(yp[2]) - T(ym[2])) * i2y) + (T(zp[3]) - T(zm[3])) * i2z;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const T ax = f[1] > 0.f ? (T(f[c]) - T(xm[c])) * i1x : (T(xp[c]) - T(f[c])) * i1x;
+        const T ay = f[2] > 0.f ? (T(f[c]) - T(ym[c])) * i1y : (T(yp[c]) - T(f[c])) * i1y;
+        const T az = f[3] > 0.f ? (T(f[c]) - T(zm[c])) * i1z : (T(zp[c]) - T(f[c])) * i1z;
+        T r = dT[c] + ((T(f[1]) * ax + T(f[2]) * ay) + T(f[3]) * az);
+        if (c == 0) r += T(f[0]) * div;
+        R[c] = float(r);
+    }
+}
+
 }  // namespace physad

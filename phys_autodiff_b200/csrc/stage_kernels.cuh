@@ -140,6 +140,8 @@ struct PhysArgs {
     const float* halo_hi;
     float inv2dt, inv2hx, inv2hy, inv2hz;
     double inv2dt_d, inv2hx_d, inv2hy_d, inv2hz_d;  // exact-residual mode (DPRES)
+    float inv1hx, inv1hy, inv1hz;                   // 1/h: one-sided differences of the upwind scheme
+    double inv1hx_d, inv1hy_d, inv1hz_d;
     float scale_s, scale_u;
     const float* s_m; const float* s_0; const float* s_p;
     const float* u_m; const float* u_0; const float* u_p;
@@ -165,7 +167,7 @@ __device__ __forceinline__ int nb1(int v, int n, bool periodic) {
     return v < 0 ? 0 : (v >= n ? n - 1 : v);
 }
 
-template <bool WRITE_R, bool REDUCE, bool SCALE, bool DPRES>
+template <bool WRITE_R, bool REDUCE, bool SCALE, bool DPRES, bool UPWIND = false>
 __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
     using real = typename std::conditional<DPRES, double, float>::type;
     const real i2t = DPRES ? real(a.inv2dt_d) : real(a.inv2dt), i2x = DPRES ? real(a.inv2hx_d) : real(a.inv2hx);
@@ -211,16 +213,30 @@ __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
                 ntp[c] = __ldg(fp[c] + pzn); ntm[c] = __ldg(fm[c] + pzn);
                 nhi[c] = __ldg(plane_above(a, f0[c], c, zn, pln, per) + oc);
             }
-            real dT[4], gx[4], gy[4], gz[4];
+            real dT[4];
             float R[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                dT[c] = central_diff(tp[c], tm[c], i2t);
-                gx[c] = central_diff(__ldg(f0[c] + pz + oxp), __ldg(f0[c] + pz + oxm), i2x);
-                gy[c] = central_diff(__ldg(f0[c] + pz + oyp), __ldg(f0[c] + pz + oym), i2y);
-                gz[c] = central_diff(hi[c], lo[c], i2z);
+            for (int c = 0; c < 4; ++c) dT[c] = central_diff(tp[c], tm[c], i2t);
+            if (UPWIND) {
+                float xm[4], xp[4], ym[4], yp[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    xp[c] = __ldg(f0[c] + pz + oxp); xm[c] = __ldg(f0[c] + pz + oxm);
+                    yp[c] = __ldg(f0[c] + pz + oyp); ym[c] = __ldg(f0[c] + pz + oym);
+                }
+                point_residual_upwind<real>(mid, xm, xp, ym, yp, lo, hi, dT,
+                                            DPRES ? real(a.inv1hx_d) : real(a.inv1hx), DPRES ? real(a.inv1hy_d) : real(a.inv1hy),
+                                            DPRES ? real(a.inv1hz_d) : real(a.inv1hz), i2x, i2y, i2z, R);
+            } else {
+                real gx[4], gy[4], gz[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    gx[c] = central_diff(__ldg(f0[c] + pz + oxp), __ldg(f0[c] + pz + oxm), i2x);
+                    gy[c] = central_diff(__ldg(f0[c] + pz + oyp), __ldg(f0[c] + pz + oym), i2y);
+                    gz[c] = central_diff(hi[c], lo[c], i2z);
+                }
+                point_residual(mid, gx, gy, gz, dT, R);
             }
-            point_residual(mid, gx, gy, gz, dT, R);
             if (WRITE_R) {
                 const size_t i = pz + oc;
                 if (a.R[0]) a.R[0][i] = SCALE ? a.scale_s * R[0] : R[0];

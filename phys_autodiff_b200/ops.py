@@ -65,6 +65,11 @@ class Context:
         True: in double exactly as the CPU reference (bit-identical residuals, ~5 % slower)."""
         return bool(self._lib.physad_set_exact_residuals(self._h, C.c_int(int(on))))
 
+    def set_advection(self, upwind: bool) -> bool:
+        """Advection scheme of the stage-wise physics operators: False = central (the reference), True = first-order
+        upwind (additive switch).  Returns the previous setting."""
+        return bool(self._lib.physad_set_advection(self._h, C.c_int(int(upwind))))
+
     def set_fused_variant(self, v: int) -> int:
         return int(self._lib.physad_set_fused_variant(self._h, C.c_int(v)))
 

@@ -488,6 +488,49 @@ def test_fused_repeatability_stress(ctx, checker, shape, H, per):
         ctx.set_fused_variant(0)
 
 
+@pytest.mark.parametrize("shape,per,h,dt", [((40, 24, 13), True, (1, 1, 1), 2e-3), ((33, 18, 7), False, (0.5, 0.25, 2.0), 1e-2),
+                                             ((256, 16, 9), True, (1, 1, 1), 1e-2), ((1, 1, 1), True, (1, 1, 1), 1e-2)])
+def test_upwind_advection_switch(ctx, port, shape, per, h, dt):
+    """The additive upwind switch of the stage-wise operators (physad_set_advection) against oracle.c's restatement:
+    default fp32 arithmetic within the north-star tolerance, exact (double) mode to the last float bit; the loss is the
+    double sum of those residuals; the fused kernel and the closed loop refuse while it is selected."""
+    from phys_autodiff_b200 import PhysadError
+    rng = np.random.default_rng(11)
+    og = OGrid(*shape, *h, dt, per)
+    g, N = _g(og), og.N
+    f = [rng.uniform(-1, 1, n).astype(np.float32) for n in (N, N, N, 3 * N, 3 * N, 3 * N)]
+    want = port.phys_residuals_upwind(og, f)
+    central = port.phys_residuals(og, f)
+    assert ctx.set_advection(True) is False
+    try:
+        got = ctx.phys_residuals_host(g, f)
+        for a, b in zip(got, want):
+            assert max_rel_to_max(a, b) <= TOL_FIELD
+        if N > 1:
+            assert any(max_rel_to_max(a, b) > 1e-3 for a, b in zip(got, central))     # it is a different scheme
+        ls, lu, R = ctx.phys_loss_host(g, _pw(1.3, 0.7), f, want_residuals=True)
+        s0 = 1.3 * np.sum(R[0].astype(np.float64) ** 2) / N
+        s1 = 0.7 * sum(np.sum(r.astype(np.float64) ** 2) for r in R[1:]) / N
+        assert abs(ls - s0) <= 1e-6 * s0 + 1e-30 and abs(lu - s1) <= 1e-6 * s1 + 1e-30
+        ctx.set_exact_residuals(True)
+        try:
+            for a, b in zip(ctx.phys_residuals_host(g, f), want):
+                assert bits_equal(a, b)
+        finally:
+            ctx.set_exact_residuals(False)
+        huge = f[:3] + [(1e6 * a).astype(np.float32) for a in f[3:]]
+        assert all(np.all(np.isfinite(r)) for r in ctx.phys_residuals_host(g, huge))
+        w = port.mlp_random_init(32, 777, 0.25)
+        with pytest.raises(PhysadError):
+            ctx.fused_loss_host(g, _cfg(32), *w, _pw(), 0.25, dt)
+        with pytest.raises(PhysadError):
+            ctx.fused_loss_grad_host(g, _cfg(32), *w, _pw(), 0.25, dt)
+    finally:
+        assert ctx.set_advection(False) is True
+    for a, b in zip(ctx.phys_residuals_host(g, f), central):
+        assert max_rel_to_max(a, b) <= TOL_FIELD
+
+
 def test_slab_partials_sum_to_whole(ctx, checker):
     """Multi-GPU arithmetic on one GPU: slabs for world sizes 2/3/8 (halo planes recomputed, incl. the
     periodic wrap for the first/last slab) reproduce the whole-grid residuals and sums."""

@@ -172,3 +172,36 @@ def test_edge_cases_on_oracle(port):
     u = np.concatenate([np.ones(6, np.float32), np.zeros(12, np.float32)])
     Rs, *_ = port.phys_residuals(g, (s, s, s, u, u, u))
     assert list(Rs) == [1.0, 2.0, 2.0, 2.0, 2.0, 1.0]
+
+
+def test_upwind_switch_properties(port):
+    """The additive upwind-advection switch (REQUIREMENT.md:123-134, never shipped by the reference -- parity unpinned,
+    oracle.c is its only statement).  The plan's own acceptance criteria: (1) consistent with the central scheme for
+    small velocities -- the two differ only in u . grad(f), so the difference is linear in the velocity scale;
+    (2) first-order accurate: on a smooth manufactured field the deviation from the central (second-order) residual
+    halves with the grid spacing; (3) finite on large random velocity fields."""
+    rng = np.random.default_rng(3)
+    g = Grid(24, 20, 16, 0.5, 0.25, 1.0, 1e-2, True)
+    N = g.N
+    base = [rng.uniform(-1, 1, n).astype(np.float32) for n in (N, N, N, 3 * N, 3 * N, 3 * N)]
+
+    def diff(eps):
+        f = [base[0], base[1], base[2]] + [(eps * a).astype(np.float32) for a in base[3:]]
+        c, u = port.phys_residuals(g, f), port.phys_residuals_upwind(g, f)
+        return max(float(np.max(np.abs(a.astype(np.float64) - b))) for a, b in zip(c, u))
+    d1, d2, d3 = diff(1.0), diff(1e-1), diff(1e-2)
+    assert d1 > 0 and d2 <= 0.2 * d1 and d3 <= 0.2 * d2          # -> 0 with the velocity (linear for sigma, quadratic for u)
+    errs = []
+    for n in (32, 64):
+        h = 2 * math.pi / n
+        gm = Grid(n, 8, 8, h, h, h, 1e-3, True)
+        f = manufactured_fields(gm, 0.3, kx=1, ky=0, kz=0, const_u=True)   # varies along x only: periodic for every n
+        c, u = port.phys_residuals(gm, f), port.phys_residuals_upwind(gm, f)
+        errs.append(float(np.max(np.abs(c[0].astype(np.float64) - u[0]))))
+    assert 0.4 <= errs[1] / errs[0] <= 0.6, errs                  # O(h)
+    big = [base[0], base[1], base[2]] + [(1e6 * a).astype(np.float32) for a in base[3:]]
+    assert all(np.all(np.isfinite(r)) for r in port.phys_residuals_upwind(g, big))
+    # clamped faces: a clamped neighbour is the point itself, the one-sided difference vanishes there
+    gc = Grid(5, 4, 3, 1, 1, 1, 1e-2, False)
+    f = [rng.uniform(-1, 1, n).astype(np.float32) for n in (60, 60, 60, 180, 180, 180)]
+    assert all(np.all(np.isfinite(r)) for r in port.phys_residuals_upwind(gc, f))
