@@ -162,6 +162,22 @@ int physad_phys_loss_host(physad_ctx* ctx, const physad_grid* g, const physad_ph
                           const float* u_tp1, float* loss_sigma, float* loss_u, float* R_sigma, float* R_ux,
                           float* R_uy, float* R_uz);
 
+/* ---- reduced-precision field I/O (ADDITIVE: the reference plans it, REQUIREMENT.md:123-128 -- "inputs / outputs may be
+ * FP16, differences and reductions keep FP32 accumulation" -- and never ships it) ------------------------------------
+ * The six physics input fields live in HBM as 16-bit elements (dtype PHYSAD_F16 = IEEE half, PHYSAD_BF16 = bfloat16; same
+ * layouts as above, element count unchanged): physad_mlp_generate_fields_lp_dev rounds the strict-fp32 MLP outputs to
+ * nearest-even on the store, physad_phys_loss_lp_dev widens every load to fp32 and then runs the fp32 stencil, the double
+ * reduction and (optionally) fp32 residual outputs unchanged: 24 instead of 48 B/point of input traffic.  Whole grid,
+ * central scheme, nx % 4 == 0, 8-byte aligned field arrays.  What the rounding costs: with the reference's dt = 2e-3 the
+ * time difference multiplies the rounding error of the fields by 1/(2 dt) = 250, see profiles/r02_lowprecision_io_study.json. */
+enum { PHYSAD_F32 = 0, PHYSAD_F16 = 1, PHYSAD_BF16 = 2 };
+int physad_mlp_generate_fields_lp_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float dt, int dtype,
+                                      void* sigma_tm1, void* sigma_t, void* sigma_tp1, void* u_tm1, void* u_t, void* u_tp1,
+                                      void* stream);
+int physad_phys_loss_lp_dev(physad_ctx* ctx, const physad_grid* g, int dtype, const void* sigma_tm1, const void* sigma_t,
+                            const void* sigma_tp1, const void* u_tm1, const void* u_t, const void* u_tp1, double* acc_dev,
+                            float* R_sigma, float* R_ux, float* R_uy, float* R_uz, void* stream);
+
 /* The same on one rank's z-slab of supplied fields (multi-GPU): the six arrays
  * hold only the slab's planes (sigma_*: n, u_*: 3n channel-major, n = slab points); halo_lo / halo_hi
  * ([4 channels: sigma_t, ux_t, uy_t, uz_t][ny][nx] each, device) are the time-t planes just below / above the

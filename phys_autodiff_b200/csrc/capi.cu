@@ -405,7 +405,7 @@ int launch_fused(physad_ctx* c, const physad_grid* g, const physad_slab& s, floa
 // ---- MLP over the grid ---------------------------------------------------------------------
 template <int H, bool FIELDS>
 int launch_grid_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], GridInferArgs a,
-                  cudaStream_t st) {
+                  cudaStream_t st, int dtype = PHYSAD_F32) {
     const int nzl = s.z_end - s.z_begin;
     if (nzl == 0) return 0;
     if (nzl > 65535) return fail(PHYSAD_E_UNSUPPORTED, "grid MLP kernels: more than 65535 planes per call");
@@ -414,7 +414,9 @@ int launch_grid_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, con
     MlpConst<H> k;
     fill_const<H>(c, tc, k);
     const dim3 grid(unsigned((g->nx + 31) / 32), unsigned((g->ny + 31) / 32), unsigned(nzl));
-    k_mlp_grid<H, FIELDS, 2><<<grid, 256, 0, st>>>(k, a);
+    if (FIELDS && dtype == PHYSAD_F16) k_mlp_grid<H, FIELDS, 2, __half><<<grid, 256, 0, st>>>(k, a);
+    else if (FIELDS && dtype == PHYSAD_BF16) k_mlp_grid<H, FIELDS, 2, __nv_bfloat16><<<grid, 256, 0, st>>>(k, a);
+    else k_mlp_grid<H, FIELDS, 2><<<grid, 256, 0, st>>>(k, a);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -422,21 +424,21 @@ int launch_grid_t(physad_ctx* c, const physad_grid* g, const physad_slab& s, con
 
 template <bool FIELDS>
 int launch_grid(physad_ctx* c, const physad_grid* g, const physad_slab& s, const float tc[3], GridInferArgs a,
-                cudaStream_t st) {
+                cudaStream_t st, int dtype = PHYSAD_F32) {
     a.nx = g->nx; a.ny = g->ny; a.nz = g->nz;
     a.z_begin = s.z_begin; a.z_end = s.z_end;
     a.m1p1 = c->cfg.norm == 1;
     switch (template_h(c->cfg.H)) {
-        case 32: return launch_grid_t<32, FIELDS>(c, g, s, tc, a, st);
-        case 64: return launch_grid_t<64, FIELDS>(c, g, s, tc, a, st);
-        case 128: return launch_grid_t<128, FIELDS>(c, g, s, tc, a, st);
+        case 32: return launch_grid_t<32, FIELDS>(c, g, s, tc, a, st, dtype);
+        case 64: return launch_grid_t<64, FIELDS>(c, g, s, tc, a, st, dtype);
+        case 128: return launch_grid_t<128, FIELDS>(c, g, s, tc, a, st, dtype);
     }
     return fail(PHYSAD_E_UNSUPPORTED, "H > 128 not built");
 }
 
 // ---- physics on supplied fields --------------------------------------------------------------
 template <bool WRITE_R, bool REDUCE, bool SCALE>
-int launch_phys(physad_ctx* c, const physad_grid* g_in, PhysArgs a, cudaStream_t st, int slab_planes = -1) {
+int launch_phys(physad_ctx* c, const physad_grid* g_in, PhysArgs a, cudaStream_t st, int slab_planes = -1, int dtype = PHYSAD_F32) {
     // slab mode: the arrays hold `slab_planes` planes and the z neighbours outside them come from a.halo_lo/hi
     physad_grid gl = *g_in;
     if (slab_planes >= 0) gl.nz = slab_planes;
@@ -453,10 +455,12 @@ int launch_phys(physad_ctx* c, const physad_grid* g_in, PhysArgs a, cudaStream_t
     const bool upwind = c->advection == 1;
     // 128-bit form when rows are quad-aligned and wide enough to fill the 64-quad blocks reasonably (central scheme only)
     static const bool no_v4 = getenv("PHYSAD_NO_V4") != nullptr;  // tuning aid
-    bool v4 = !upwind && !no_v4 && g->nx % 4 == 0 && g->nx >= 128;
+    bool v4 = !upwind && !no_v4 && g->nx % 4 == 0 && (g->nx >= 128 || dtype != PHYSAD_F32);
     const void* ptrs[12] = {a.s_m, a.s_0, a.s_p, a.u_m, a.u_0, a.u_p, a.R[0], a.R[1], a.R[2], a.R[3], a.halo_lo, a.halo_hi};
-    for (const void* p : ptrs) v4 = v4 && (uintptr_t(p) % 16 == 0);
+    for (int k = 0; k < 12; ++k) v4 = v4 && (uintptr_t(ptrs[k]) % ((dtype != PHYSAD_F32 && (k < 6 || k >= 10)) ? 8 : 16) == 0);
     v4 = v4 && (size_t(g->nx) * g->ny * g->nz) % 4 == 0;  // channel stride of the u arrays
+    if (dtype != PHYSAD_F32 && (!v4 || SCALE || c->exact_residuals))
+        return fail(PHYSAD_E_UNSUPPORTED, "16-bit fields: need nx % 4 == 0, 8-byte aligned arrays, the central scheme and fp32 residual arithmetic");
     if (v4) {
         const unsigned tx = unsigned((g->nx + 255) / 256), ty = unsigned((g->ny + V4_THREADS / 64 - 1) / (V4_THREADS / 64));
         if (ty > 65535u) return fail(PHYSAD_E_UNSUPPORTED, "phys kernels: ny > 131070");
@@ -470,7 +474,12 @@ int launch_phys(physad_ctx* c, const physad_grid* g_in, PhysArgs a, cudaStream_t
             if (int rc = ensure_partials(c, size_t(tx) * ty * nch)) return rc;
             a.partials = c->partials; a.ticket = c->ticket;
         }
-        if (c->exact_residuals) k_phys_residual_v4<WRITE_R, REDUCE, SCALE, true><<<grid, V4_THREADS, 0, st>>>(a);
+        if constexpr (!SCALE) {
+            if (dtype == PHYSAD_F16) k_phys_residual_v4<WRITE_R, REDUCE, SCALE, false, __half><<<grid, V4_THREADS, 0, st>>>(a);
+            else if (dtype == PHYSAD_BF16) k_phys_residual_v4<WRITE_R, REDUCE, SCALE, false, __nv_bfloat16><<<grid, V4_THREADS, 0, st>>>(a);
+        }
+        if (dtype != PHYSAD_F32) { }
+        else if (c->exact_residuals) k_phys_residual_v4<WRITE_R, REDUCE, SCALE, true><<<grid, V4_THREADS, 0, st>>>(a);
         else k_phys_residual_v4<WRITE_R, REDUCE, SCALE, false><<<grid, V4_THREADS, 0, st>>>(a);
         c->launches++;
         CU(cudaGetLastError());
@@ -1026,6 +1035,40 @@ int physad_phys_loss_dev(physad_ctx* c, const physad_grid* g, const float* s_m, 
     a.acc_out = acc;
     if (Rs || Rx || Ry || Rz) return launch_phys<true, true, false>(c, g, a, cudaStream_t(stream));
     return launch_phys<false, true, false>(c, g, a, cudaStream_t(stream));
+}
+
+// ---- reduced-precision field I/O (additive) ----------------------------------------------------------------------
+int physad_mlp_generate_fields_lp_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, float t, float dt, int dtype,
+                                      void* s_m, void* s_0, void* s_p, void* u_m, void* u_0, void* u_p, void* stream) {
+    if (!c || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p) return fail(PHYSAD_E_INVALID, "generate_fields_lp: null argument");
+    if (dtype != PHYSAD_F16 && dtype != PHYSAD_BF16) return fail(PHYSAD_E_INVALID, "generate_fields_lp: dtype must be PHYSAD_F16 or PHYSAD_BF16");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = need_4x4(c, "generate_fields_lp")) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    DeviceGuard dg(c->device);
+    const float ts[3] = {t - dt, t, t + dt};
+    const float tc[3] = {time_coord(ts[0], c->cfg.norm), time_coord(ts[1], c->cfg.norm), time_coord(ts[2], c->cfg.norm)};
+    GridInferArgs a{};
+    a.sigma[0] = static_cast<float*>(s_m); a.sigma[1] = static_cast<float*>(s_0); a.sigma[2] = static_cast<float*>(s_p);
+    a.u[0] = static_cast<float*>(u_m); a.u[1] = static_cast<float*>(u_0); a.u[2] = static_cast<float*>(u_p);
+    return launch_grid<true>(c, g, s, tc, a, cudaStream_t(stream), dtype);
+}
+
+int physad_phys_loss_lp_dev(physad_ctx* c, const physad_grid* g, int dtype, const void* s_m, const void* s_0, const void* s_p,
+                            const void* u_m, const void* u_0, const void* u_p, double* acc, float* Rs, float* Rx, float* Ry,
+                            float* Rz, void* stream) {
+    if (!c || !s_m || !s_0 || !s_p || !u_m || !u_0 || !u_p || !acc) return fail(PHYSAD_E_INVALID, "phys_loss_lp: null argument");
+    if (dtype != PHYSAD_F16 && dtype != PHYSAD_BF16) return fail(PHYSAD_E_INVALID, "phys_loss_lp: dtype must be PHYSAD_F16 or PHYSAD_BF16");
+    if (int rc = check_grid(g)) return rc;
+    const bool any = Rs || Rx || Ry || Rz, all = Rs && Rx && Ry && Rz;
+    if (any && !all) return fail(PHYSAD_E_INVALID, "phys_loss_lp: residual outputs must be all set or all null");
+    DeviceGuard dg(c->device);
+    auto f = [](const void* p) { return static_cast<const float*>(p); };   // element type travels in `dtype`
+    PhysArgs a = phys_args(f(s_m), f(s_0), f(s_p), f(u_m), f(u_0), f(u_p), Rs, Rx, Ry, Rz);
+    a.acc_out = acc;
+    if (any) return launch_phys<true, true, false>(c, g, a, cudaStream_t(stream), -1, dtype);
+    return launch_phys<false, true, false>(c, g, a, cudaStream_t(stream), -1, dtype);
 }
 
 int physad_phys_loss_slab_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, const float* s_m,

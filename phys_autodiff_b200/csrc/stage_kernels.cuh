@@ -4,9 +4,35 @@
 // These are the device-resident, HBM-facing halves of the path; the metric kernel is in
 // fused_loss.cuh.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "fused_loss.cuh"
 
 namespace physad {
+
+// Reduced-precision field I/O (additive, REQUIREMENT.md:123-128 "FP16/BF16: inputs / outputs may be 16-bit, differences and
+// reductions accumulate in FP32"): the fields live in HBM as __half or __nv_bfloat16, every load widens to fp32 and the
+// arithmetic after the load is the fp32 kernels' unchanged.  E = float is the reference path.
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldg4(const __half* p) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 ldg4(const __nv_bfloat16* p) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float ldg1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldg1(const __half* p) { return __half2float(__ldg(p)); }
+__device__ __forceinline__ float ldg1(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 
 // ---------------------------------------------------------------------------------------------
 // MLP over the grid, coordinates from the point index (reference: make_grid_coords +
@@ -31,7 +57,7 @@ struct GridInferArgs {
 // Block = 32 x 8 threads on a 32 x 32 (x,y) patch of one z plane; a thread evaluates 4 points that share x
 // (rows ty, ty+8, ...), which shares b1 + W1[h,0]x and W1[h,2]z between them exactly as in the fused kernel;
 // coordinates come from the index tables (no per-point integer or IEEE division); stores are coalesced rows.
-template <int H, bool FIELDS, int UNROLL>
+template <int H, bool FIELDS, int UNROLL, typename E = float>
 __global__ void __launch_bounds__(256) k_mlp_grid(const __grid_constant__ MlpConst<H> w, const GridInferArgs a) {
     constexpr int P = 4;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -53,10 +79,12 @@ __global__ void __launch_bounds__(256) k_mlp_grid(const __grid_constant__ MlpCon
                 const size_t i = (size_t(blockIdx.z) * a.ny + y) * a.nx + x;
 #pragma unroll
                 for (int s = 0; s < 3; ++s) {
-                    a.sigma[s][i] = o[j][s][0];
-                    a.u[s][i] = o[j][s][1];
-                    a.u[s][n + i] = o[j][s][2];
-                    a.u[s][2 * n + i] = o[j][s][3];
+                    E* ps = reinterpret_cast<E*>(a.sigma[s]);   // E != float: the six arrays hold 16-bit elements
+                    E* pu = reinterpret_cast<E*>(a.u[s]);
+                    st1(ps + i, o[j][s][0]);
+                    st1(pu + i, o[j][s][1]);
+                    st1(pu + n + i, o[j][s][2]);
+                    st1(pu + 2 * n + i, o[j][s][3]);
                 }
             }
         }
@@ -150,14 +178,16 @@ struct PhysArgs {
 };
 
 // time-t plane just below / above plane z of channel c (see PhysArgs::halo_lo/hi)
-__device__ __forceinline__ const float* plane_below(const PhysArgs& a, const float* f0c, int c, int z, size_t pln, bool per) {
+template <typename E>
+__device__ __forceinline__ const E* plane_below(const PhysArgs& a, const E* f0c, int c, int z, size_t pln, bool per) {
     if (z > 0) return f0c + size_t(z - 1) * pln;
-    if (a.halo_lo) return a.halo_lo + size_t(c) * pln;
+    if (a.halo_lo) return reinterpret_cast<const E*>(a.halo_lo) + size_t(c) * pln;
     return f0c + size_t((per && !a.clamp_z) ? a.nz - 1 : 0) * pln;
 }
-__device__ __forceinline__ const float* plane_above(const PhysArgs& a, const float* f0c, int c, int z, size_t pln, bool per) {
+template <typename E>
+__device__ __forceinline__ const E* plane_above(const PhysArgs& a, const E* f0c, int c, int z, size_t pln, bool per) {
     if (z + 1 < a.nz) return f0c + size_t(z + 1) * pln;
-    if (a.halo_hi) return a.halo_hi + size_t(c) * pln;
+    if (a.halo_hi) return reinterpret_cast<const E*>(a.halo_hi) + size_t(c) * pln;
     return f0c + size_t((per && !a.clamp_z) ? 0 : a.nz - 1) * pln;
 }
 
@@ -268,11 +298,10 @@ __global__ void __launch_bounds__(256) k_phys_residual(const PhysArgs a) {
 // what the latency-bound scalar form lacks.  Needs nx % 4 == 0 and 16-byte aligned arrays (capi.cu checks
 // and otherwise uses k_phys_residual).  Block = 64 quads (256 columns) x 2 rows (V4_THREADS = 128).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 constexpr int V4_THREADS = 128;   // 64 quads x 2 rows: ~170 registers per thread, so three small blocks fit an SM where one of 256 did
-template <bool WRITE_R, bool REDUCE, bool SCALE, bool DPRES>
+template <bool WRITE_R, bool REDUCE, bool SCALE, bool DPRES, typename E = float>
 __global__ void __launch_bounds__(V4_THREADS, DPRES ? 2 : 3) k_phys_residual_v4(const PhysArgs a) {
     using real = typename std::conditional<DPRES, double, float>::type;
     const real i2t = DPRES ? real(a.inv2dt_d) : real(a.inv2dt), i2x = DPRES ? real(a.inv2hx_d) : real(a.inv2hx);
@@ -288,9 +317,10 @@ __global__ void __launch_bounds__(V4_THREADS, DPRES ? 2 : 3) k_phys_residual_v4(
         const size_t row = size_t(y) * a.nx;
         const size_t oc = row + x, oxm = row + nb1(x - 1, a.nx, per), oxp = row + nb1(x + 4, a.nx, per);
         const size_t oym = size_t(nb1(y - 1, a.ny, per)) * a.nx + x, oyp = size_t(nb1(y + 1, a.ny, per)) * a.nx + x;
-        const float* f0[4] = {a.s_0, a.u_0, a.u_0 + N, a.u_0 + 2 * N};
-        const float* fm[4] = {a.s_m, a.u_m, a.u_m + N, a.u_m + 2 * N};
-        const float* fp[4] = {a.s_p, a.u_p, a.u_p + N, a.u_p + 2 * N};
+        auto el = [](const float* p) { return reinterpret_cast<const E*>(p); };   // the fields hold elements of type E
+        const E* f0[4] = {el(a.s_0), el(a.u_0), el(a.u_0) + N, el(a.u_0) + 2 * N};
+        const E* fm[4] = {el(a.s_m), el(a.u_m), el(a.u_m) + N, el(a.u_m) + 2 * N};
+        const E* fp[4] = {el(a.s_p), el(a.u_p), el(a.u_p) + N, el(a.u_p) + 2 * N};
         float4 lo[4], mid[4], hi[4];
         {
             const size_t pc = size_t(z0) * pln + oc;
@@ -308,8 +338,8 @@ __global__ void __launch_bounds__(V4_THREADS, DPRES ? 2 : 3) k_phys_residual_v4(
                 tm[c] = ldg4(fm[c] + pz + oc);
                 yp[c] = ldg4(f0[c] + pz + oyp);
                 ym[c] = ldg4(f0[c] + pz + oym);
-                xl[c] = __ldg(f0[c] + pz + oxm);
-                xr[c] = __ldg(f0[c] + pz + oxp);
+                xl[c] = ldg1(f0[c] + pz + oxm);
+                xr[c] = ldg1(f0[c] + pz + oxp);
             }
             float4 Rv[4];
 #pragma unroll

@@ -169,6 +169,36 @@ class Context:
                                                        self._stream()), "mlp_generate_fields")
         return s[0], s[1], s[2], u[0], u[1], u[2]
 
+    # -- reduced-precision field I/O (additive) ---------------------------------------------------------
+    @staticmethod
+    def _lp(dtype):
+        import torch
+        return {"f16": (1, torch.float16), "bf16": (2, torch.bfloat16)}[dtype]
+
+    def mlp_generate_fields_lp(self, g: Grid, t: float, dt: float, dtype: str = "bf16", slab=None):
+        """The six fields as 16-bit device tensors (dtype 'f16' | 'bf16'): strict-fp32 MLP, rounded to nearest-even on the store."""
+        code, td = self._lp(dtype)
+        cs, n = self._slab(g, slab)
+        s = [self._empty(n, td) for _ in range(3)]
+        u = [self._empty(3 * n, td) for _ in range(3)]
+        cg = g.c()
+        check(self._lib.physad_mlp_generate_fields_lp_dev(self._h, C.byref(cg), C.byref(cs), C.c_float(t), C.c_float(dt), C.c_int(code),
+                                                          ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(u[0]), ptr(u[1]), ptr(u[2]),
+                                                          self._stream()), "mlp_generate_fields_lp")
+        return s[0], s[1], s[2], u[0], u[1], u[2]
+
+    def phys_loss_lp_acc(self, g: Grid, fields: Sequence, dtype: str = "bf16", want_residuals: bool = False):
+        """Loss sums (and fp32 residuals) from 16-bit fields; arithmetic after the load is the fp32 path's."""
+        import torch
+        code, td = self._lp(dtype)
+        assert all(f.dtype == td for f in fields)
+        acc = self._empty(2, torch.float64)
+        R = [self._empty(g.N) for _ in range(4)] if want_residuals else [None] * 4
+        cg = g.c()
+        check(self._lib.physad_phys_loss_lp_dev(self._h, C.byref(cg), C.c_int(code), *[ptr(f) for f in fields], ptr(acc),
+                                                *[ptr(r) for r in R], self._stream()), "phys_loss_lp")
+        return (acc, tuple(R)) if want_residuals else acc
+
     # -- deeper MLPs (additive, BASELINE config 5) -----------------------------------------------------
     def set_weights_deep(self, cfg: MLPConfig, hidden_layers: int, W1, b1, Wh, bh, W2, b2) -> None:
         """L = hidden_layers >= 1 hidden layers of width H; Wh: (L-1) x [H x H] row-major, bh: (L-1) x H."""

@@ -531,6 +531,43 @@ def test_upwind_advection_switch(ctx, port, shape, per, h, dt):
         assert max_rel_to_max(a, b) <= TOL_FIELD
 
 
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+def test_reduced_precision_field_io(ctx, port, dtype):
+    """16-bit field I/O of the stage-wise path (additive, REQUIREMENT.md:123-128): the stored fields are the strict-fp32
+    MLP outputs rounded to nearest-even; the loss kernel widens them to fp32 and is then the fp32 kernel -- bitwise the
+    same residuals as the fp32 kernel run on the widened values, and within the north-star tolerance of the CPU
+    restatement on those values."""
+    import torch
+    from phys_autodiff_b200 import PhysadError
+    td = {"f16": torch.float16, "bf16": torch.bfloat16}[dtype]
+    og = OGrid(64, 24, 9, 1, 1, 1, 2e-3, True)
+    g = _g(og)
+    ctx.set_weights(_cfg(64), *port.mlp_random_init(64, 777, 0.25))
+    f32 = ctx.mlp_generate_fields(g, 0.25, 2e-3)
+    flp = ctx.mlp_generate_fields_lp(g, 0.25, 2e-3, dtype)
+    for a, b in zip(f32, flp):
+        assert b.dtype == td and torch.equal(b, a.to(td))
+    wide = [x.float() for x in flp]
+    acc, R = ctx.phys_loss_lp_acc(g, flp, dtype, want_residuals=True)
+    acc32, R32 = ctx.phys_loss_acc(g, wide, want_residuals=True)
+    assert all(torch.equal(a, b) for a, b in zip(R, R32))
+    assert torch.allclose(acc, acc32, rtol=1e-12, atol=0)      # (narrow rows take the scalar fp32 kernel: another summation order)
+    want = port.phys_residuals(og, [x.cpu().numpy() for x in wide])
+    for a, b in zip(R, want):
+        assert max_rel_to_max(a.cpu().numpy(), b) <= TOL_FIELD
+    assert torch.equal(ctx.phys_loss_lp_acc(g, flp, dtype), acc)          # loss only: same sums
+    s0 = float(torch.sum(R[0].double() ** 2))
+    assert abs(float(acc[0]) - s0) <= 1e-9 * s0
+    # a z-slab of the fields
+    fs = ctx.mlp_generate_fields_lp(g, 0.25, 2e-3, dtype, slab=(2, 7))
+    plane = og.nx * og.ny
+    assert torch.equal(fs[1], flp[1][2 * plane: 7 * plane])
+    og2 = OGrid(30, 8, 4, 1, 1, 1, 2e-3, True)                            # nx % 4 != 0: no 16-bit form
+    f2 = ctx.mlp_generate_fields_lp(_g(og2), 0.25, 2e-3, dtype)
+    with pytest.raises(PhysadError):
+        ctx.phys_loss_lp_acc(_g(og2), f2, dtype)
+
+
 def test_slab_partials_sum_to_whole(ctx, checker):
     """Multi-GPU arithmetic on one GPU: slabs for world sizes 2/3/8 (halo planes recomputed, incl. the
     periodic wrap for the first/last slab) reproduce the whole-grid residuals and sums."""
