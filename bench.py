@@ -42,7 +42,7 @@ def ncu_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the committed
     `ncu --set full` capture of this same command (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_fused_default_summary.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_fused_default_summary.json")) as fh:
             d = json.load(fh)[0]
         unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
