@@ -444,6 +444,23 @@ def main():
                 del fields
         extra["depth_sweep"] = sweep
         ctx.set_weights(cfg, *w)
+        # the analytic (forward-mode tangent) loss: north_star's literal wording, additive and NOT the parity path --
+        # a different discretisation of the same PDE (no finite differences), FFMA arithmetic, one network evaluation
+        tacc = ctx.tangent_loss_acc(g, T0)
+        for _ in range(3):
+            ctx.tangent_loss_acc(g, T0, acc=tacc)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record(); ctx.tangent_loss_acc(g, T0, acc=tacc); e1.record()
+        torch.cuda.synchronize()
+        tms = statistics.median(e0.elapsed_time(e1) for e0, e1 in evs)
+        tl = ctx.finalize(tacc.cpu().numpy(), pw, g.N)
+        extra["analytic_tangent_loss_not_parity"] = {
+            "value": g.N / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms, "loss": {"sigma": float(tl[0]), "u": float(tl[1])},
+            "ffma_tflops": 2 * 25 * H * g.N / (tms * 1e-3) / 1e12, "frac_of_ffma_peak": 2 * 25 * H * g.N / (tms * 1e-3) / 1e12 / peak_ffma,
+            "note": "forward-mode derivatives through the MLP instead of finite differences (physad_tangent_loss_dev); "
+                    "different discretisation: its loss is not comparable bit-for-bit with the metric's"}
         # the closed loop (additive): losses + d(L_sigma + L_u)/d(weights) per step, device-resident
         pwc = PhysWeights(1.0, 1.0)
         gacc, ggrad = ctx.fused_loss_grad_acc(g, pwc, T0, DT)

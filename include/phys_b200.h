@@ -25,6 +25,12 @@ void mlp_phys_loss_fused_cuda(const GridSpec& g, const MLPGridConfig& cfg, const
                               float t, float dt, float* out_loss_sigma, float* out_loss_u, float* opt_R_sigma = nullptr,
                               float* opt_R_ux = nullptr, float* opt_R_uy = nullptr, float* opt_R_uz = nullptr);
 
+// The same PDE loss with the derivatives PROPAGATED THROUGH the MLP in forward mode instead of finite differences
+// (BASELINE north-star's literal wording).  Additive and not the reference's arithmetic: the reference differences MLP
+// outputs on the grid (src/phys_cpu.cpp:71-93), so the two losses differ by the discretisation error.  In = Out = 4, H <= 128.
+void mlp_phys_loss_tangent_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, const PhysWeights& pw, float t,
+                                float* out_loss_sigma, float* out_loss_u);
+
 // The closed loop the reference plans in REQUIREMENT.md:155-169 ("MLP backward: pass dL/dsigma, dL/du to the MLP
 // weights") and stops short of (cpu_phys_loss_backward returns dL/dR only): the two losses of the MLP-generated
 // fields AND d(L_sigma + L_u)/d(weights), the loss VJP carried through the transposed stencil and the MLP on the

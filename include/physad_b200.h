@@ -267,6 +267,22 @@ void physad_finalize_loss(const double acc[2], const physad_phys_weights* w, siz
 void physad_mlp_random_init(int In, int H, int Out, unsigned int seed, float scale, float* W1, float* b1, float* W2,
                             float* b2);
 
+/* ---- analytic ("tangent") loss (ADDITIVE, explicitly NOT the parity path) --------------------------------------------
+ * BASELINE.json's north_star in its literal wording: the input-derivatives are PROPAGATED THROUGH the MLP (forward mode,
+ * dy/dx, dy/dy, dy/dz, dy/dt per point in registers) and the PDE residuals of src/phys_cpu.cpp:103-106 are formed from them
+ * -- no finite differences, no second and third network evaluation, no halo.  The reference never does this (every
+ * derivative there is a central difference of outputs sampled on the grid), so the result
+ * differs from physad_fused_loss_dev by the discretisation error; the checker is oracle.c: oracle_tangent_loss (unpinned).
+ * Space derivatives are with respect to the physical coordinate x = i*hx of the normalised network input.  acc_dev[2]
+ * receives {sum R_sigma^2, sum |R_u|^2} over the slab (finalise with physad_finalize_loss after a multi-rank sum);
+ * R_* (device, slab-local) optional.  Requires In = Out = 4, H <= 128. */
+int physad_tangent_loss_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, double* acc_dev,
+                            float* R_sigma, float* R_ux, float* R_uy, float* R_uz, void* stream);
+/* Host-buffer form on the whole grid: (optionally) new weights in, the two losses out. */
+int physad_tangent_loss_host(physad_ctx* ctx, const physad_grid* g, const physad_mlp_config* cfg, const float* W1, const float* b1,
+                             const float* W2, const float* b2, const physad_phys_weights* w, float t, float* loss_sigma,
+                             float* loss_u);
+
 /* ---- closed loop (ADDITIVE: the reference plans it, REQUIREMENT.md:155-169, but stops at dL/dR,
  * src/phys_cpu.cpp:151-170, and its MLP backward is the MSE one, src/mlp_cpu.cpp:38-85) ----------------
  * Loss of the MLP-generated fields AND the gradient of L_sigma + L_u (weights w included, mean over N) with

@@ -152,6 +152,19 @@ class _Oracle:
 class PortOracle(_Oracle):
     kind = "port"
 
+    def tangent_loss(self, g: Grid, w, t, m1p1=True, want_residuals=False):
+        """Analytic forward-mode physics loss (additive, parity unpinned) -> dict(acc_sigma, acc_u[, R])."""
+        W1, b1, W2, b2 = w
+        a_s, a_u = C.c_double(), C.c_double()
+        R = [np.empty(g.N, np.float32) for _ in range(4)] if want_residuals else [None] * 4
+        f = self.lib.oracle_tangent_loss; f.restype = None
+        f(C.byref(g.c()), C.c_int(b1.size), C.c_int(int(m1p1)), _fp(W1), _fp(b1), _fp(W2), _fp(b2), C.c_float(t),
+          C.byref(a_s), C.byref(a_u), *[_fp(r) for r in R])
+        out = dict(acc_sigma=a_s.value, acc_u=a_u.value)
+        if want_residuals:
+            out["R"] = tuple(R)
+        return out
+
     def phys_residuals_upwind(self, g: Grid, fields):
         """First-order upwind advection (additive switch, parity unpinned: oracle.c is the only statement of it)."""
         N = g.N

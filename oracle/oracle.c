@@ -378,6 +378,56 @@ void oracle_phys_residuals_upwind(const oracle_grid* g, const float* s_m, const 
 #undef LIN
 }
 
+/* Analytic ("tangent") loss -- PARITY UNPINNED, there is no reference implementation: the reference differences MLP
+ * outputs on the grid (src/phys_cpu.cpp:71-93), this propagates the input-derivatives through the network in forward
+ * mode (BASELINE.json north_star's literal wording; include/physad_b200.h: physad_tangent_loss_dev).  The hidden
+ * pre-activation z_h is formed in fp32 exactly as the forward path does (src/mlp_cpu.cpp:19-22), so the ReLU mask is the
+ * forward's; everything after it is in double.  Space derivatives refer to the physical coordinate x = i*hx of the
+ * normalised input c = norm(i/(n-1)): dc/dx = (2 or 1) / ((n-1) hx).  Writes the four residual arrays (may be null) and
+ * the two double sums. */
+void oracle_tangent_loss(const oracle_grid* g, int H, int m1p1, const float* W1, const float* b1, const float* W2, const float* b2,
+                         float t, double* acc_s, double* acc_u, float* Rs, float* Rx, float* Ry, float* Rz) {
+    const int nx = g->nx, ny = g->ny, nz = g->nz;
+    const double f = m1p1 ? 2.0 : 1.0;
+    const double s[3] = {nx > 1 ? f / ((double)(nx - 1) * (double)g->hx) : 0.0, ny > 1 ? f / ((double)(ny - 1) * (double)g->hy) : 0.0,
+                         nz > 1 ? f / ((double)(nz - 1) * (double)g->hz) : 0.0};
+    const float ct = m1p1 ? t : t + 0.5f; /* src/mlp_grid.cpp:38 */
+    double as = 0.0, au = 0.0;
+    size_t i = 0;
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x, ++i) {
+                const float c[4] = {axis_coord(x, nx, m1p1), axis_coord(y, ny, m1p1), axis_coord(z, nz, m1p1), ct};
+                double yv[4], J[4][4];
+                for (int o = 0; o < 4; ++o) {
+                    yv[o] = (double)b2[o];
+                    for (int k = 0; k < 4; ++k) J[o][k] = 0.0;
+                }
+                for (int h = 0; h < H; ++h) {
+                    float zh = b1[h];
+                    for (int k = 0; k < 4; ++k) zh += W1[h * 4 + k] * c[k];
+                    if (zh > 0.f)
+                        for (int o = 0; o < 4; ++o) {
+                            yv[o] += (double)W2[o * H + h] * (double)zh;
+                            for (int k = 0; k < 4; ++k) J[o][k] += (double)W2[o * H + h] * (double)W1[h * 4 + k];
+                        }
+                }
+                double gr[4][3];
+                for (int o = 0; o < 4; ++o)
+                    for (int j = 0; j < 3; ++j) gr[o][j] = J[o][j] * s[j];
+                const double div = gr[1][0] + gr[2][1] + gr[3][2];
+                double R[4];
+                for (int o = 0; o < 4; ++o) R[o] = J[o][3] + (yv[1] * gr[o][0] + yv[2] * gr[o][1] + yv[3] * gr[o][2]);
+                R[0] += yv[0] * div;
+                const float r[4] = {(float)R[0], (float)R[1], (float)R[2], (float)R[3]};
+                if (Rs) { Rs[i] = r[0]; Rx[i] = r[1]; Ry[i] = r[2]; Rz[i] = r[3]; }
+                as += (double)r[0] * r[0];
+                au += (double)r[1] * r[1] + (double)r[2] * r[2] + (double)r[3] * r[3];
+            }
+    *acc_s = as;
+    *acc_u = au;
+}
+
 /* Sum of squares over a point range, sequential in double as src/phys_cpu.cpp:140-145. */
 void oracle_sumsq(const float* Rs, const float* Rx, const float* Ry, const float* Rz, size_t i0, size_t i1, double* acc_s,
                   double* acc_u) {

@@ -6,6 +6,7 @@
 #include "dense_kernels.cuh"
 #include "grad_kernels.cuh"
 #include "stage_kernels.cuh"
+#include "tangent_kernels.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -1272,6 +1273,92 @@ int physad_fused_loss_allreduce_dev(physad_ctx* c, const physad_grid* g, const p
     DeviceGuard dg(c->device);
     float* R[4] = {Rs, Rx, Ry, Rz};
     return launch_fused(c, g, s, t, dt, acc, R, cudaStream_t(stream), true);
+}
+
+// ---- analytic (tangent) loss: derivatives propagated through the MLP in forward mode (additive, NOT the parity path) ----
+}  // extern "C"  (templates below)
+namespace {
+template <int H>
+void fill_tangent(const physad_ctx* c, float tcoord, TangentConst<H>& k) {
+    const int h_rt = c->cfg.H;
+    for (int h = 0; h < H; ++h) {
+        const bool on = h < h_rt;
+        const float w1[4] = {on ? c->W1[size_t(h) * 4] : 0.f, on ? c->W1[size_t(h) * 4 + 1] : 0.f, on ? c->W1[size_t(h) * 4 + 2] : 0.f,
+                             on ? c->W1[size_t(h) * 4 + 3] : 0.f};
+        volatile float pt = w1[3] * tcoord;   // separately rounded product, as MlpConst::pt0
+        k.w1[h] = make_float4(w1[0], w1[1], w1[2], float(pt));
+        k.b1[h] = on ? c->b1[h] : 0.f;        // padded units: z = 0, mask 0, contribute nothing
+        float w2[4];
+        for (int o = 0; o < 4; ++o) w2[o] = on ? c->W2[size_t(o) * h_rt + h] : 0.f;
+        k.w2[h] = make_float4(w2[0], w2[1], w2[2], w2[3]);
+        for (int o = 0; o < 4; ++o) k.p[h][o] = make_float4(w2[o] * w1[0], w2[o] * w1[1], w2[o] * w1[2], w2[o] * w1[3]);
+    }
+    k.b2 = make_float4(c->b2[0], c->b2[1], c->b2[2], c->b2[3]);
+}
+
+template <int H>
+int launch_tangent_t(physad_ctx* c, const TangentArgs& a, float tcoord, int blocks, cudaStream_t st) {
+    TangentConst<H> k;
+    fill_tangent<H>(c, tcoord, k);
+    CU(cudaError_t(tangent_launch(H, &k, a, blocks, st)));
+    c->launches++;
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+int physad_tangent_loss_dev(physad_ctx* c, const physad_grid* g, const physad_slab* slab, float t, double* acc, float* Rs,
+                            float* Rx, float* Ry, float* Rz, void* stream) {
+    if (!c || !acc) return fail(PHYSAD_E_INVALID, "tangent_loss: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = need_4x4(c, "tangent_loss")) return rc;
+    physad_slab s;
+    if (int rc = check_slab(g, slab, &s)) return rc;
+    const bool any = Rs || Rx || Ry || Rz, all = Rs && Rx && Ry && Rz;
+    if (any && !all) return fail(PHYSAD_E_INVALID, "tangent_loss: residual outputs must be all set or all null");
+    DeviceGuard dg(c->device);
+    cudaStream_t st = cudaStream_t(stream);
+    if (s.z_end == s.z_begin) {
+        CU(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+        return 0;
+    }
+    if (int rc = ensure_coord_tables(c, g, st)) return rc;
+    TangentArgs a{};
+    a.nx = g->nx; a.ny = g->ny; a.nz = g->nz; a.z_begin = s.z_begin; a.z_end = s.z_end;
+    a.cxs = c->tab.dev; a.cys = a.cxs + g->nx; a.czs = a.cys + g->ny;
+    // dc/dx of a coordinate c = norm(i / (n - 1)) sampled at x = i h:  MinusOneToOne 2 / ((n-1) h), ZeroToOne 1 / ((n-1) h)
+    const double f = c->cfg.norm == 1 ? 2.0 : 1.0;
+    a.sx = g->nx > 1 ? float(f / (double(g->nx - 1) * double(g->hx))) : 0.f;
+    a.sy = g->ny > 1 ? float(f / (double(g->ny - 1) * double(g->hy))) : 0.f;
+    a.sz = g->nz > 1 ? float(f / (double(g->nz - 1) * double(g->hz))) : 0.f;
+    const size_t n = size_t(s.z_end - s.z_begin) * g->ny * g->nx;
+    const int blocks = int(std::max<size_t>(1, std::min<size_t>(size_t(c->sm_count) * 2, (n + 2 * TANGENT_THREADS - 1) / (2 * TANGENT_THREADS))));
+    if (int rc = ensure_partials(c, size_t(blocks))) return rc;
+    a.partials = c->partials; a.ticket = c->ticket; a.acc_out = acc;
+    a.R[0] = Rs; a.R[1] = Rx; a.R[2] = Ry; a.R[3] = Rz;
+    const float tc = time_coord(t, c->cfg.norm);
+    switch (template_h(c->cfg.H)) {
+        case 32: return launch_tangent_t<32>(c, a, tc, blocks, st);
+        case 64: return launch_tangent_t<64>(c, a, tc, blocks, st);
+        case 128: return launch_tangent_t<128>(c, a, tc, blocks, st);
+    }
+    return fail(PHYSAD_E_UNSUPPORTED, "H > 128 not built");
+}
+
+int physad_tangent_loss_host(physad_ctx* c, const physad_grid* g, const physad_mlp_config* cfg, const float* W1, const float* b1,
+                             const float* W2, const float* b2, const physad_phys_weights* w, float t, float* loss_sigma,
+                             float* loss_u) {
+    if (!c || !w) return fail(PHYSAD_E_INVALID, "tangent_loss: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (cfg) {
+        if (int rc = physad_set_weights(c, cfg, W1, b1, W2, b2)) return rc;
+    }
+    DeviceGuard dg(c->device);
+    if (int rc = physad_tangent_loss_dev(c, g, nullptr, t, c->d_acc, nullptr, nullptr, nullptr, nullptr, c->stream)) return rc;
+    CU(cudaMemcpyAsync(c->h_acc, c->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    physad_finalize_loss(c->h_acc, w, size_t(g->nx) * g->ny * g->nz, loss_sigma, loss_u);
+    return 0;
 }
 
 // ---- closed loop: loss and its gradient with respect to the MLP weights (additive, grad_kernels.cuh) ----

@@ -270,6 +270,17 @@ void mlp_phys_loss_fused_cuda(const GridSpec& g, const MLPGridConfig& cfg, const
         die("mlp_phys_loss_fused_cuda", rc);
 }
 
+void mlp_phys_loss_tangent_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, const PhysWeights& pw, float t,
+                                float* out_loss_sigma, float* out_loss_u) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const physad_grid cg = to_c(g);
+    const physad_phys_weights cw = to_c(pw);
+    const physad_mlp_config mc{int(cfg.dims.In), int(cfg.dims.H), int(cfg.dims.Out), norm_of(cfg.norm)};
+    if (int rc = physad_tangent_loss_host(ctx(), &cg, &mc, w.W1.data(), w.b1.data(), w.W2.data(), w.b2.data(), &cw, t,
+                                          out_loss_sigma, out_loss_u))
+        die("mlp_phys_loss_tangent_cuda", rc);
+}
+
 void mlp_phys_loss_grad_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, const PhysWeights& pw,
                              float t, float dt, float* out_loss_sigma, float* out_loss_u, MLPWeights& grad) {
     std::lock_guard<std::mutex> lk(g_mu);

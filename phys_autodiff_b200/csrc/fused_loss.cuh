@@ -241,7 +241,7 @@ __device__ __forceinline__ void grid_reduce2(double a, double b, double2* partia
 
 // Exchange-only launch for a rank whose slab is empty (more ranks than planes): it still has to
 // contribute its zeros and must end up with the global sums.
-__global__ void k_xchg_only(const __grid_constant__ XchgArgs x, double* out, HostResult* host, unsigned long long host_seq,
+static __global__ void k_xchg_only(const __grid_constant__ XchgArgs x, double* out, HostResult* host, unsigned long long host_seq,
                             unsigned int* status) {
     double a = 0.0, b = 0.0;
     const bool ok = xchg_allreduce2(x, a, b);

@@ -405,6 +405,20 @@ class Context:
         ls, lu = self.finalize(self._read_acc(acc), pw, g.N)
         return (ls, lu, tuple(R)) if want_residuals else (ls, lu)
 
+    # -- analytic (tangent) loss: additive, NOT the parity path ---------------------------------------------
+    def tangent_loss_acc(self, g: Grid, t: float, slab=None, acc=None, residuals=None):
+        """Forward-mode derivatives through the MLP instead of finite differences (include/physad_b200.h); returns the
+        device sums {sum Rs^2, sum |Ru|^2} of the slab."""
+        import torch
+        cs, _ = self._slab(g, slab)
+        if acc is None:
+            acc = self._empty(2, torch.float64)
+        R = residuals if residuals is not None else [None] * 4
+        cg = g.c()
+        check(self._lib.physad_tangent_loss_dev(self._h, C.byref(cg), C.byref(cs), C.c_float(t), ptr(acc),
+                                                *[ptr(r) for r in R], self._stream()), "tangent_loss")
+        return acc
+
     # -- closed loop: loss + gradient with respect to the MLP weights (additive) ----------------------------
     def fused_loss_grad_acc(self, g: Grid, pw: PhysWeights, t: float, dt: float, acc=None, grad=None):
         """Device form: returns (acc[2], grad[9H+4]) float64 device tensors; grad = dW1 | db1 | dW2 | db2."""
@@ -625,6 +639,19 @@ def cuda_phys_loss_backward_fused(g: Grid, pw: PhysWeights, fields):
 
 def mlp_phys_loss_fused_cuda(g: Grid, cfg: MLPConfig, w, pw: PhysWeights, t: float, dt: float, want_residuals: bool = False):
     return default_context().fused_loss_host(g, cfg, *w, pw, t, dt, want_residuals)
+
+
+def mlp_phys_loss_tangent_cuda(g: Grid, cfg: MLPConfig, w, pw: PhysWeights, t: float):
+    """Analytic forward-mode physics loss (additive, NOT the parity path): (L_sigma, L_u) with derivatives propagated
+    through the MLP instead of finite differences."""
+    c = default_context()
+    W1, b1, W2, b2 = (_f32(a) for a in w)
+    ls, lu = C.c_float(), C.c_float()
+    cg, cc, cw = g.c(), cfg.c(), pw.c()
+    check(c._lib.physad_tangent_loss_host(c._h, C.byref(cg), C.byref(cc), ptr(W1), ptr(b1), ptr(W2), ptr(b2), C.byref(cw),
+                                          C.c_float(t), C.byref(ls), C.byref(lu)), "tangent_loss_host")
+    c.cfg = cfg
+    return np.float32(ls.value), np.float32(lu.value)
 
 
 def mlp_phys_loss_grad_cuda(g: Grid, cfg: MLPConfig, w, pw: PhysWeights, t: float, dt: float):

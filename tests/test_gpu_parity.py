@@ -568,6 +568,35 @@ def test_reduced_precision_field_io(ctx, port, dtype):
         ctx.phys_loss_lp_acc(_g(og2), f2, dtype)
 
 
+@pytest.mark.parametrize("shape,H,m1p1,h", [((48, 40, 12), 64, True, (1, 1, 1)), ((33, 18, 7), 32, False, (0.5, 0.25, 2.0)),
+                                              ((70, 37, 5), 128, True, (1, 1, 1)), ((1, 1, 1), 16, True, (1, 1, 1)),
+                                              ((128, 64, 32), 64, True, (1, 1, 1))])
+def test_tangent_loss_matches_its_checker(ctx, port, shape, H, m1p1, h):
+    """The analytic forward-mode loss (additive; north_star's literal wording; NOT the parity path) against its checker
+    oracle_tangent_loss (masks from the same fp32 pre-activations, the rest in double): residuals to 1e-5 of the largest,
+    sums to 1e-6; z-slabs sum to the whole; repeatable."""
+    import torch
+    from phys_autodiff_b200.ops import slab_for_rank
+    og = OGrid(*shape, *h, 2e-3, True)
+    g = _g(og)
+    w = port.mlp_random_init(H, 777, 0.25)
+    want = port.tangent_loss(og, w, 0.25, m1p1, want_residuals=True)
+    ctx.set_weights(_cfg(H, m1p1), *w)
+    R = [torch.empty(og.N, device="cuda") for _ in range(4)]
+    acc = ctx.tangent_loss_acc(g, 0.25, residuals=R).cpu().numpy()
+    for a, b in zip(R, want["R"]):
+        assert max_rel_to_max(a.cpu().numpy(), b) <= TOL_FIELD
+    assert abs(acc[0] - want["acc_sigma"]) <= 1e-6 * want["acc_sigma"] + 1e-30
+    assert abs(acc[1] - want["acc_u"]) <= 1e-6 * want["acc_u"] + 1e-30
+    assert np.array_equal(ctx.tangent_loss_acc(g, 0.25).cpu().numpy(), acc)
+    hl = _ops().mlp_phys_loss_tangent_cuda(g, _cfg(H, m1p1), w, _pw(1.3, 0.7), 0.25)      # host-buffer form
+    assert hl == ctx.finalize(acc, _pw(1.3, 0.7), og.N)
+    tot = np.zeros(2)
+    for r in range(3):
+        tot += ctx.tangent_loss_acc(g, 0.25, slab=slab_for_rank(og.nz, r, 3)).cpu().numpy()
+    assert np.allclose(tot, acc, rtol=1e-12)
+
+
 def test_slab_partials_sum_to_whole(ctx, checker):
     """Multi-GPU arithmetic on one GPU: slabs for world sizes 2/3/8 (halo planes recomputed, incl. the
     periodic wrap for the first/last slab) reproduce the whole-grid residuals and sums."""

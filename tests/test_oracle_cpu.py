@@ -205,3 +205,36 @@ def test_upwind_switch_properties(port):
     gc = Grid(5, 4, 3, 1, 1, 1, 1e-2, False)
     f = [rng.uniform(-1, 1, n).astype(np.float32) for n in (60, 60, 60, 180, 180, 180)]
     assert all(np.all(np.isfinite(r)) for r in port.phys_residuals_upwind(gc, f))
+
+
+def test_tangent_loss_checker_agrees_with_finite_differences_where_the_network_is_affine(port):
+    """The analytic (forward-mode) loss is an additive, non-parity mode; its checker (oracle_tangent_loss) is pinned the
+    only way it can be: where every hidden unit is active over the whole domain the network is affine in (x,y,z,t), central
+    differences of it are exact, and the tangent residuals must equal the reference-pinned finite-difference residuals
+    (physical spacing h consistent with the normalisation: dc/dx * 2h = c(i+1) - c(i-1)).  With the random-init network the
+    two losses differ by the discretisation error at the ReLU kinks -- a few per cent at 48^3, shrinking with the spacing."""
+    rng = np.random.default_rng(2)
+    H = 16
+    W1 = rng.uniform(-0.2, 0.2, H * 4).astype(np.float32)
+    b1 = np.full(H, 5.0, np.float32)                                   # all units active on [-1, 1]^3 x t
+    W2 = rng.uniform(-0.3, 0.3, 4 * H).astype(np.float32)
+    b2 = rng.uniform(-0.3, 0.3, 4).astype(np.float32)
+    g = Grid(20, 12, 9, 0.7, 1.1, 0.9, 0.05, False)
+    tan = port.tangent_loss(g, (W1, b1, W2, b2), 0.25, True, want_residuals=True)
+    fd = port.fused_loss(g, (W1, b1, W2, b2), 0.25, 0.05, 1.0, 1.0, True, want_residuals=True)
+    nx, ny, nz = g.nx, g.ny, g.nz
+    inner = np.zeros((nz, ny, nx), bool)
+    inner[1:-1, 1:-1, 1:-1] = True                                     # clamped faces use one-sided halves: compare the interior
+    inner = inner.reshape(-1)
+    for a, b in zip(tan["R"], fd["R"]):
+        assert np.max(np.abs(a[inner].astype(np.float64) - b[inner])) <= 1e-3 * np.max(np.abs(b[inner]))   # fp32 noise of the differenced outputs
+    # random-init network of the benchmark: same PDE, different discretisation
+    w = port.mlp_random_init(64, 777, 0.25)
+    errs = []
+    for n in (24, 48):
+        h = 2.0 / (n - 1)                                              # physical spacing = coordinate spacing: dc/dx = 1
+        gg = Grid(n, n, n, h, h, h, 2e-3, False)
+        t1 = port.tangent_loss(gg, w, 0.25, True)
+        f1 = port.fused_loss(gg, w, 0.25, 2e-3, 1.0, 1.0, True)
+        errs.append(abs(t1["acc_u"] - f1["acc_u"]) / f1["acc_u"])
+    assert errs[1] < 0.2 and errs[1] < errs[0] + 0.02, errs
