@@ -122,7 +122,7 @@ int physad_mlp_generate_fields_host(physad_ctx* ctx, const physad_grid* g, float
                                     float* sigma_t, float* sigma_tp1, float* u_tm1, float* u_t, float* u_tp1);
 
 /* ---- deeper MLPs (ADDITIVE: BASELINE config 5, depth sweep) ------------------------------------
- * 4 -> H -> H -> ... -> H -> 4 with `hidden_layers` >= 1 hidden layers of width H (H = 32 or 64).  The
+ * 4 -> H -> H -> ... -> H -> 4 with `hidden_layers` >= 1 hidden layers of width H (H = 32, 64 or 128).  The
  * reference API has exactly one hidden layer (include/mlp.h:5-6); further layers repeat its layer rule
  * (src/mlp_cpu.cpp:19-24: from the bias, + W[g,h]*a[h] for h ascending, separate fp32 multiply and add,
  * ReLU).  There is no reference implementation for hidden_layers > 1 (parity is against oracle/oracle.c's
@@ -131,6 +131,14 @@ int physad_mlp_generate_fields_host(physad_ctx* ctx, const physad_grid* g, float
  * A later physad_set_weights() switches the context back to a one-hidden-layer network. */
 int physad_set_weights_deep(physad_ctx* ctx, const physad_mlp_config* cfg, int hidden_layers, const float* W1,
                             const float* b1, const float* Wh, const float* bh, const float* W2, const float* b2);
+/* How the hidden -> hidden layers of the deep entry points are evaluated (ADDITIVE; default 0).
+ *   0: strict fp32 on the CUDA cores -- bit-identical to the CPU restatement (the parity mode);
+ *   1: tcgen05 tensor cores, every fp32 operand split into three bf16 terms, six term products accumulated in fp32
+ *      (deep_tc_kernels.cuh): NOT bit-exact -- outputs agree with mode 0 to ~1e-6 relative, the error class of an
+ *      FFMA-contracted evaluation such as the reference's own CUDA kernels (src/mlp_cuda.cu).  Needs hidden_layers >= 2 and
+ *      all layer images resident in shared memory (H = 128: <= 3 hidden layers; H = 64: <= 9; H = 32: <= 16); other
+ *      shapes return PHYSAD_E_UNSUPPORTED from the deep calls while mode 1 is selected.  Layer 1 stays strict. */
+int physad_set_deep_mode(physad_ctx* ctx, int mode);
 /* Stage-wise evaluation over the grid (coordinates from the index); outputs as the one-layer calls above. */
 int physad_mlp_grid_infer_deep_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float* out,
                                    void* stream);

@@ -3,6 +3,7 @@
 // decides shapes, fills the kernel-parameter weight block and moves bytes.
 #include "../../include/physad_b200.h"
 #include "deep_kernels.cuh"
+#include "deep_tc_kernels.cuh"
 #include "dense_kernels.cuh"
 #include "grad_kernels.cuh"
 #include "stage_kernels.cuh"
@@ -78,6 +79,10 @@ struct physad_ctx {
     int deep_layers = 0;          // L (0 = not set)
     float *d_wh = nullptr, *d_bh = nullptr;
     size_t d_wh_cap = 0, d_bh_cap = 0;
+    int deep_mode = 0;            // 0: strict fp32 on the CUDA cores; 1: hidden layers on tcgen05 (three-term bf16, deep_tc_kernels.cu)
+    bool deep_tc_ok = false;      // the current deep weights have operand images
+    uint8_t* d_wparts = nullptr;  // operand images of the hidden->hidden layers for mode 1 (null: shape not supported there)
+    size_t d_wparts_cap = 0;
     // per-kernel launch facts on THIS device (opt-in shared memory set, resident blocks per SM): function
     // attributes are per device, so they are cached per context, not per process
     std::unordered_map<const void*, int> blocks_per_sm;
@@ -598,6 +603,14 @@ int launch_deep(physad_ctx* c, const physad_grid* g, const physad_slab& s, const
     for (int k3 = 0; k3 < 3; ++k3) a.tc[k3] = tc[k3];
     MlpConst<H> k;
     fill_const<H>(c, tc, k);
+    if (c->deep_mode == 1) {
+        if (!deep_tc_supported(H, c->deep_layers) || !c->deep_tc_ok)
+            return fail(PHYSAD_E_UNSUPPORTED, "deep fast mode: needs >= 2 hidden layers whose operand images fit in shared memory "
+                                              "(H = 128: <= 3 hidden layers, H = 64: <= 9)");
+        CU(cudaError_t(deep_tc_launch(H, FIELDS, &k, a, c->d_wparts, c->sm_count, st)));
+        c->launches++;
+        return 0;
+    }
     // persistent grid: one 256-thread block per SM, tiles of 64..768 points handed out round-robin (deep_kernels.cu)
     CU(cudaError_t(deep_launch(H, FIELDS, &k, a, c->sm_count, st)));
     c->launches++;
@@ -677,7 +690,7 @@ int physad_ctx_destroy(physad_ctx* c) {
     cudaFree(c->xbuf);
     cudaFree(c->plan.dev);
     cudaFree(c->tab.dev);
-    cudaFree(c->d_wh); cudaFree(c->d_bh);
+    cudaFree(c->d_wh); cudaFree(c->d_bh); cudaFree(c->d_wparts);
     cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->d_acc); cudaFree(c->scratch);
     cudaFree(c->gws); cudaFree(c->gpart); cudaFree(c->d_grad);
     if (c->h_grad) cudaFreeHost(c->h_grad);
@@ -951,13 +964,34 @@ int physad_set_weights_deep(physad_ctx* c, const physad_mlp_config* cfg, int hid
         CU(cudaMalloc(&c->d_bh, nb * sizeof(float)));
         c->d_bh_cap = nb;
     }
+    // fast mode (physad_set_deep_mode): every layer as three bf16 terms in the MMA's shared-memory layout
+    std::vector<uint8_t> images;
+    if (deep_tc_supported(int(H), hidden_layers)) {
+        images.resize(nl * deep_tc_layer_bytes(int(H)));
+        for (size_t l = 0; l < nl; ++l) deep_tc_pack_layer(int(H), Wh + l * H * H, images.data() + l * deep_tc_layer_bytes(int(H)));
+        if (images.size() > c->d_wparts_cap) {
+            if (c->d_wparts) CU(cudaFree(c->d_wparts));
+            c->d_wparts = nullptr; c->d_wparts_cap = 0;
+            CU(cudaMalloc(&c->d_wparts, images.size()));
+            c->d_wparts_cap = images.size();
+        }
+    }
     CU(cudaDeviceSynchronize());   // kernels of ANY stream may still read the previous layers
     if (nl) {
         CU(cudaMemcpy(c->d_wh, wt.data(), nl * H * H * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_bh, bh, nl * H * sizeof(float), cudaMemcpyHostToDevice));
+        if (!images.empty()) CU(cudaMemcpy(c->d_wparts, images.data(), images.size(), cudaMemcpyHostToDevice));
     }
+    c->deep_tc_ok = !images.empty();
     CU(cudaDeviceSynchronize());   // ... and the copies have landed before a kernel on a non-blocking stream can start
     c->deep_layers = hidden_layers;
+    return 0;
+}
+
+int physad_set_deep_mode(physad_ctx* c, int mode) {
+    if (!c) return fail(PHYSAD_E_INVALID, "set_deep_mode: null context");
+    if (mode != 0 && mode != 1) return fail(PHYSAD_E_INVALID, "set_deep_mode: 0 (strict fp32) or 1 (tensor cores, three-term bf16)");
+    c->deep_mode = mode;
     return 0;
 }
 

@@ -211,6 +211,10 @@ class Context:
               "set_weights_deep")
         self.cfg = cfg
 
+    def set_deep_mode(self, mode: int) -> None:
+        """0: strict fp32 (bit-exact, default); 1: hidden layers on the tensor cores with three-term bf16 operands (~1e-6)."""
+        check(self._lib.physad_set_deep_mode(self._h, C.c_int(mode)), "set_deep_mode")
+
     def mlp_grid_infer_deep(self, g: Grid, t: float, slab=None):
         cs, n = self._slab(g, slab)
         out = self._empty(n * 4)
