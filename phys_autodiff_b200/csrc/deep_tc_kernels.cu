@@ -1,26 +1,33 @@
 // Deeper coordinate MLPs, fast mode: hidden -> hidden layers on tcgen05 with three-term bf16 operands.
 // What is computed, and why it is additive / not bit-exact: deep_tc_kernels.cuh.
 //
-// One 256-thread block per SM, persistent over tiles of 128 points; the three time slices of a tile go through the
-// layers one after the other ("row" = (point, slice), 128 rows = the M of one MMA).
-//   * thread (m, half): row m = its tensor-memory lane (warp w may touch lanes 32 (w % 4) ..), half = w / 4 picks which
-//     H/2 hidden units it produces in layer 1 and which H/2 accumulator columns it drains after a layer;
-//   * tensor memory columns: [0, H) the fp32 accumulators D; then the three bf16 terms of the A operand (activations),
-//     H/2 columns each, two K elements per 32-bit column -- written by tcgen05.st from the thread that owns the row, so
-//     activations never visit shared memory and no proxy fence is needed between an epilogue and the next layer;
-//   * shared memory: the operand images of ALL hidden -> hidden layers (3 terms x H x H bf16 each, K-major no-swizzle core
-//     matrices, written by deep_tc_pack_layer on the host and bulk-copied once per block), the layer-1 pairs, the output
-//     layer, the biases;
-//   * a layer = 6 (term pairs) x H/16 (K slices) tcgen05.mma issued by thread 0, smallest products first, then ONE
-//     tcgen05.commit -> mbarrier; every thread waits on it, drains its columns (tcgen05.ld), adds the bias, applies
-//     ReLU and either splits into the next layer's terms or, after the last hidden layer, accumulates the four outputs.
+// One 288-thread block per SM, persistent over "row tiles" = 128 points x one time slice (row = (point, slice), 128 rows =
+// the M of an MMA).  Warp-specialised, ONE row tile in flight, pipelined across the two halves of the hidden width:
+//   * warps 0-3 ("group 0") and 4-7 ("group 1"): thread m of a group owns row m = tensor-memory lane m (a warp may only
+//     touch lanes 32 (w % 4) ..); group g produces hidden units [g H/2, (g+1) H/2) in layer 1 and drains accumulator
+//     columns of the same range after every layer;  warp 8: lane 0 issues every MMA, the warp owns the tensor memory;
+//   * tensor memory columns: [0, H) the fp32 accumulators D (halves D0 | D1), then TWO A operands (activations) of
+//     3 bf16 terms x H/2 columns each (two K elements per 32-bit column), written by tcgen05.st from the thread that
+//     owns the row: activations never visit shared memory.  Layer t reads A[t & 1], its epilogue writes A[(t+1) & 1];
+//   * shared memory: the operand images of ALL hidden -> hidden layers (3 terms x H x H bf16 each, K-major no-swizzle
+//     core matrices, written by deep_tc_pack_layer on the host and bulk-copied once per block), layer-1 pairs, output
+//     layer, biases;
+//   * a layer = four blocks (N half n, K half k) of 6 term pairs x H/32 K slices, issued n0k0 n0k1 | commit full[0] |
+//     n1k0 n1k1 | commit full[1].  Block (n, k) of the NEXT layer needs only "group k has written its K half of the
+//     other A operand and group n has drained D_n" = mbarrier ready[k] / ready[n] (128 arrivals each), so group 0's
+//     epilogue runs under this layer's n1 blocks and group 1's under the next layer's n0k0 block: the tensor pipe only
+//     waits when an epilogue takes longer than a quarter of a layer;
+//   * after the last hidden layer a group accumulates its share of the four outputs (fp32 FMA) instead of splitting;
+//     the next row tile's layer 1 is computed BEFORE waiting for that last layer (its A operand is free), so it is off
+//     the critical path as well.  Group 0 hands its partial outputs to group 1 through shared memory; group 1 stores.
 // Governing roofline: the bf16 tensor pipe at 6 MMA passes per fp32-equivalent contraction: 2 H^2 x 6 flop per row and
-// layer against MEASURED_PEAKS' dense bf16 figure.  This first version runs MMA and epilogue of a tile back to back
-// (one accumulator, one A operand), so the tensor pipe idles while the CUDA cores split activations and vice versa.
+// layer against MEASURED_PEAKS' dense bf16 figure.
 #include "deep_tc_kernels.cuh"
 #include "mlp_eval.cuh"
 #include "tc_common.cuh"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace physad {
@@ -29,44 +36,69 @@ namespace {
 
 using namespace tc;
 
-constexpr int TC_THREADS = 256;
 constexpr int TILE = 128;                       // rows of one MMA
+// epilogue warps per (group, lane quarter): each takes 1/WPG of the group's columns.  Two for H >= 64: the epilogues are
+// latency-bound with one (measured: tensor pipe waiting 25 % of the time), a thread's share must stay a multiple of 16.
+template <int H>
+struct Wpg { static constexpr int value = H >= 64 ? 2 : 1; };
+template <int H>
+struct TcThreads { static constexpr int value = (8 * Wpg<H>::value + 1) * 32; };   // 2 groups x 4 lane quarters x WPG warps + the MMA warp
 constexpr size_t MIN_SMEM = 120 * 1024;         // more than half an SM's shared memory: exactly one block per SM, so the
                                                 // block's tensor-memory allocation can never wait for a neighbour's
 
 template <int H>
-struct TmemCols { static constexpr uint32_t value = H == 128 ? 512u : (H == 64 ? 256u : 128u); };   // >= H + 3 H/2, a power of two
+struct TmemCols { static constexpr uint32_t value = H == 128 ? 512u : (H == 64 ? 256u : 128u); };   // = H + 2 * 3 H/2
 
 template <int H>
 size_t smem_for(int nl) {
-    return size_t(nl) * 3 * H * H * 2 + 20 * H + 16 * H + size_t(nl) * H * 4 + TILE * 16 + 32;
+    return size_t(nl) * 3 * H * H * 2 + 20 * H + 16 * H + size_t(nl) * H * 4 + 2 * 3 * TILE * 16 + 64;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int H, bool FIELDS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-    k_mlp_deep_tc(const __grid_constant__ MlpConst<H> w, const __grid_constant__ DeepArgs a, const uint8_t* __restrict__ wparts) {
+__global__ void __launch_bounds__(TcThreads<H>::value, 1)
+    k_mlp_deep_tc(const __grid_constant__ MlpConst<H> w, const __grid_constant__ DeepArgs a, const uint8_t* __restrict__ wparts,
+                  unsigned long long* __restrict__ prof) {
     constexpr int NS = FIELDS ? 3 : 1;
-    constexpr int HH = H / 2;                    // hidden units per thread in layer 1 = accumulator columns per thread
-    constexpr uint32_t D_COL = 0, A_COL = H;     // A term p: columns A_COL + p * H/2 ...
+    constexpr int HH = H / 2;                    // hidden units / accumulator columns per group; columns of one A term
+    constexpr uint32_t D_COL = 0, A_COL = H, A_BUF = 3 * HH;   // A operand b, term p: columns A_COL + b A_BUF + p HH ...
     constexpr uint32_t LBO = 16 * H, SBO = 128;  // K-neighbour / N-neighbour core matrices of a weight image
     constexpr uint32_t TERM_BYTES = H * H * 2;
+    constexpr int KS_HALF = H / 32;              // K = 16 slices per K half
+    constexpr int WPG = Wpg<H>::value, TC_THREADS = TcThreads<H>::value, MMA_WARP = 8 * WPG;
+    constexpr int CPT = HH / WPG;                // hidden units / accumulator columns per epilogue thread
+    constexpr int NCH = CPT / 16;                // ... in chunks of 16
+    static_assert(CPT % 16 == 0, "an epilogue thread drains whole 16-column chunks");
     extern __shared__ __align__(128) uint8_t smem[];
     const int nl = a.hidden_layers - 1;
     const size_t w_bytes = size_t(nl) * 3 * TERM_BYTES;
     float2* s_l1 = reinterpret_cast<float2*>(smem + w_bytes);                      // [5][H/2], as deep_kernels.cu
     float4* s_w2 = reinterpret_cast<float4*>(smem + w_bytes + 20 * H);             // {W2[0..3, h]}
     float* s_bh = reinterpret_cast<float*>(smem + w_bytes + 36 * H);               // [nl][H]
-    float4* s_part = reinterpret_cast<float4*>(smem + w_bytes + 36 * H + size_t(nl) * H * 4);   // [TILE] upper half's outputs
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + TILE);                   // [0] weights landed, [1] layer done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    float4* s_part = reinterpret_cast<float4*>(smem + w_bytes + 36 * H + size_t(nl) * H * 4);   // [2][3][TILE] partial outputs
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 3 * TILE);
+    uint64_t* bar_w = bars;                      // weights landed
+    uint64_t* bar_full = bars + 1;               // [2] D_n complete (tcgen05.commit)
+    uint64_t* bar_ready = bars + 3;              // [2] group g: K half g of the next A operand written, D_g drained
+    uint64_t* bar_part = bars + 5;               // the other threads' partial outputs of a row are in s_part
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
-    const int tid = threadIdx.x, warp = tid >> 5, m = tid & (TILE - 1), half = tid >> 7;
+    const int tid = threadIdx.x, warp = tid >> 5, m = tid & (TILE - 1);
+    const int sub = tid >> 7;                    // which CPT columns of the hidden width (2 WPG = the MMA warp)
+    const int grp = sub / WPG;                   // K half / accumulator half this thread works for
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(bar_w, 1);
+        mbar_init(&bar_full[0], 1);
+        mbar_init(&bar_full[1], 1);
+        mbar_init(&bar_ready[0], TILE * WPG);
+        mbar_init(&bar_ready[1], TILE * WPG);
+        mbar_init(bar_part, TILE * (2 * WPG - 1));
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<TmemCols<H>::value>(tmem_slot);
+    if (warp == MMA_WARP) tmem_alloc<TmemCols<H>::value>(tmem_slot);
     for (int q = tid; q < H / 2; q += TC_THREADS) {
         const float4 ra = __ldg(reinterpret_cast<const float4*>(a.W1) + 2 * q), rb = __ldg(reinterpret_cast<const float4*>(a.W1) + 2 * q + 1);
         s_l1[q] = make_float2(__ldg(a.b1 + 2 * q), __ldg(a.b1 + 2 * q + 1));
@@ -84,38 +116,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncthreads();
     fence_after_sync();
     if (tid == 0) {
-        mbar_expect_tx(&bars[0], uint32_t(w_bytes));
-        for (int i = 0; i < nl * 3; ++i) bulk_g2s(smem + size_t(i) * TERM_BYTES, wparts + size_t(i) * TERM_BYTES, TERM_BYTES, &bars[0]);
+        mbar_expect_tx(bar_w, uint32_t(w_bytes));
+        for (int i = 0; i < nl * 3; ++i) bulk_g2s(smem + size_t(i) * TERM_BYTES, wparts + size_t(i) * TERM_BYTES, TERM_BYTES, bar_w);
     }
-    mbar_wait(&bars[0], 0);
 
     const uint32_t tbase = *tmem_slot;
-    const uint32_t lane_t = tbase + (uint32_t((warp & 3) * 32) << 16);
-    const uint32_t idesc = idesc_bf16_f32(TILE, H);
     const long long n_slab = (long long)(a.z_end - a.z_begin) * a.ny * a.nx;
     const long long tiles = (n_slab + TILE - 1) / TILE;
-    const int plane = a.nx * a.ny;
-    const size_t n = size_t(n_slab);
-    const float4 b2 = w.b2;
-    uint32_t phase = 0;
+    const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long my_rts = my_tiles * NS;      // row tiles of this block, in order (tile, slice)
 
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long long i_pt = tile * TILE + m;
-        float cx, cy, cz;
+    if (warp == MMA_WARP) {
+        // ================= MMA warp: lane 0 issues, in layer order; `step` counts layers over all row tiles =================
         {
+            mbar_wait(bar_w, 0);
+            const uint32_t idesc = idesc_bf16_f32(TILE, HH);
+            const uint32_t w0 = smem_u32(smem);
+            // t3(a) t1(W), t2 t2, t1 t3, t2 t1, t1 t2, t1 t1: ascending magnitude
+            const int PA[6] = {2, 1, 0, 1, 0, 0}, PB[6] = {0, 1, 2, 0, 1, 0};
+            uint32_t ph_ready[2] = {0, 0};
+            long long step = 0;
+            const long long t_begin = clock64();
+            long long t_wait = 0;
+            for (long long rt = 0; rt < my_rts; ++rt) {
+#pragma unroll 1
+                for (int l = 0; l < nl; ++l, ++step) {
+                    const uint32_t a_in = tbase + A_COL + uint32_t(step & 1) * A_BUF;
+                    const uint32_t wl = w0 + uint32_t(l) * 3 * TERM_BYTES;
+                    const uint32_t b_lo = (wl >> 4) | ((LBO >> 4) << 16), b_hi = (SBO >> 4) | (1u << 14);   // smem_desc(), in two words
+#pragma unroll
+                    for (int nh = 0; nh < 2; ++nh) {
+#pragma unroll
+                        for (int kh = 0; kh < 2; ++kh) {
+                            // (n0,k0): ready[0];  (n0,k1): ready[1];  the n1 blocks need nothing new
+                            if (nh == 0) {
+                                const long long t0 = clock64();
+                                mbar_wait(&bar_ready[kh], ph_ready[kh]);
+                                t_wait += clock64() - t0;
+                                ph_ready[kh] ^= 1;
+                                fence_after_sync();
+                            }
+                            if (elect_one()) {
+#pragma unroll
+                                for (int ps = 0; ps < 6; ++ps) {
+#pragma unroll
+                                    for (int ks = 0; ks < KS_HALF; ++ks) {
+                                        const uint32_t kslice = uint32_t(kh * KS_HALF + ks);
+                                        const uint32_t off = PB[ps] * TERM_BYTES + uint32_t(nh) * (HH / 8) * SBO + kslice * 2 * LBO;
+                                        mma_bf16_ts(tbase + D_COL + uint32_t(nh) * HH, a_in + PA[ps] * HH + kslice * 8, b_lo + (off >> 4), b_hi,
+                                                    idesc, !(kh == 0 && ps == 0 && ks == 0));
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        if (elect_one()) mma_commit(&bar_full[nh]);
+                        __syncwarp();
+                    }
+                }
+            }
+            if (prof && blockIdx.x == 0 && tid == MMA_WARP * 32) {
+                prof[0] = (unsigned long long)(clock64() - t_begin);
+                prof[1] = (unsigned long long)t_wait;
+                prof[2] = (unsigned long long)my_rts;
+            }
+        }
+        __syncwarp();   // lanes 1-31 wait here for the issuing lane: the block barrier below is reached as a whole warp
+    } else {
+        // ================= epilogue groups ==============================================================================
+        const uint32_t lane_t = tbase + (uint32_t((warp & 3) * 32) << 16);
+        const int plane = a.nx * a.ny;
+        const size_t n = size_t(n_slab);
+        const float4 b2 = w.b2;
+        // layer 1 (strict fp32, the arithmetic of mlp_eval.cuh) of row tile rt: this group's H/2 hidden units of row m,
+        // split and stored as K half `grp` of A operand `buf`
+        auto layer1 = [&](long long rt, uint32_t buf) {
+            const long long tile = blockIdx.x + (rt / NS) * gridDim.x;
+            const int sl = int(rt % NS);
+            const long long i_pt = tile * TILE + m;
             const long long p = i_pt < n_slab ? i_pt : n_slab - 1;   // tail tile: evaluate a valid point, never stored
             const int zl = int(p / plane), rem = int(p - (long long)zl * plane);
             const int y = rem / a.nx, x = rem - y * a.nx;
-            cx = __ldg(a.cxs + x); cy = __ldg(a.cys + y); cz = __ldg(a.czs + a.z_begin + zl);
-        }
+            const float cx = __ldg(a.cxs + x), cy = __ldg(a.cys + y), cz = __ldg(a.czs + a.z_begin + zl);
+            const float tcs = FIELDS ? a.tc[sl] : a.tc[1];
 #pragma unroll 1
-        for (int s = 0; s < NS; ++s) {
-            const float tcs = FIELDS ? a.tc[s] : a.tc[1];
-            // ---- layer 1 (strict fp32, the arithmetic of mlp_eval.cuh): this thread's H/2 hidden units of row m ------------
-#pragma unroll 1
-            for (int c = 0; c < HH / 16; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 uint32_t t1[8], t2[8], t3[8];
-                const int q0 = (half * HH + c * 16) / 2;
+                const int q0 = (sub * CPT + c * 16) / 2;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int q = q0 + j;
@@ -129,62 +216,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     unpack2(add2_rn(sxyz, pack2(pt)), v0, v1);
                     split3(relu_ref(v0), relu_ref(v1), t1[j], t2[j], t3[j]);
                 }
-                const uint32_t col = lane_t + A_COL + uint32_t(q0);
+                const uint32_t col = lane_t + A_COL + buf * A_BUF + uint32_t(q0);
                 tmem_st8(col, t1);
                 tmem_st8(col + HH, t2);
                 tmem_st8(col + 2 * HH, t3);
             }
+        };
+        uint32_t ph_full = 0, ph_part = 0, ph_prev = 0;
+        long long step = 0;
+        long long t_l1 = 0, t_wfull = 0, t_drain = 0, t_out = 0, t_wprev = 0;
+        const long long e_begin = clock64();
+        if (my_rts > 0) {
+            layer1(0, 0);
             tmem_st_wait();
             fence_before_sync();
-            __syncthreads();
-
+            mbar_arrive(&bar_ready[grp]);
+        }
+        for (long long rt = 0; rt < my_rts; ++rt) {
             float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll 1
-            for (int l = 0; l < nl; ++l) {
-                if (tid == 0) {
-                    fence_after_sync();
-                    const uint32_t wl = smem_u32(smem) + uint32_t(l) * 3 * TERM_BYTES;
-                    // t3(a) t1(W), t2 t2, t1 t3, t2 t1, t1 t2, t1 t1: ascending magnitude
-                    const int PA[6] = {2, 1, 0, 1, 0, 0}, PB[6] = {0, 1, 2, 0, 1, 0};
-                    bool acc = false;
-#pragma unroll
-                    for (int ps = 0; ps < 6; ++ps) {
-#pragma unroll 1
-                        for (int ks = 0; ks < H / 16; ++ks) {
-                            const uint64_t bd = smem_desc(wl + PB[ps] * TERM_BYTES + ks * 2 * LBO, LBO, SBO);
-                            mma_bf16_ts(tbase + D_COL, tbase + A_COL + PA[ps] * HH + ks * 8, bd, idesc, acc);
-                            acc = true;
-                        }
-                    }
-                    mma_commit(&bars[1]);
+            for (int l = 0; l < nl; ++l, ++step) {
+                const bool last = l == nl - 1;
+                const uint32_t out_buf = uint32_t((step + 1) & 1);
+                // Group 0 also observes the END of the previous layer (its n1 blocks read the operand written next; group 1
+                // has seen it as its own full[1]).  One wait per layer, in order: the barrier can never be two phases ahead,
+                // because the layer after this one needs this group's next arrival on ready[0].
+                long long c0 = clock64();
+                if (grp == 0 && step > 0) {
+                    mbar_wait(&bar_full[1], ph_prev);
+                    ph_prev ^= 1;
+                    __syncwarp();
                 }
-                __syncwarp();
-                mbar_wait(&bars[1], phase);
-                phase ^= 1;
+                long long c1 = clock64();
+                t_wprev += c1 - c0;
+                // the next row tile's layer 1 goes into the A operand this (last) layer does not read, before the wait
+                if (last && rt + 1 < my_rts) layer1(rt + 1, out_buf);
+                c0 = clock64();
+                t_l1 += c0 - c1;
+                mbar_wait(&bar_full[grp], ph_full);
+                ph_full ^= 1;
                 __syncwarp();             // tcgen05.ld / .st are warp-collective: leave the polling loop together
                 fence_after_sync();
-                const bool last = l == nl - 1;
-#pragma unroll 1
-                for (int c = 0; c < HH / 16; ++c) {
-                    const int g0 = half * HH + c * 16;
-                    uint32_t r[16];
-                    tmem_ld16(lane_t + D_COL + uint32_t(g0), r);
-                    tmem_ld_wait();
+                c1 = clock64();
+                t_wfull += c1 - c0;
+                uint32_t r[NCH][16];      // all of this thread's columns in flight, one wait
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tmem_ld16(lane_t + D_COL + uint32_t(sub * CPT + c * 16), r[c]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int g0 = sub * CPT + c * 16;
                     float v[16];
                     const float4* bp = reinterpret_cast<const float4*>(s_bh + l * H + g0);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
                         const float4 b = bp[j4];
-                        v[4 * j4] = relu_ref(__uint_as_float(r[4 * j4]) + b.x);
-                        v[4 * j4 + 1] = relu_ref(__uint_as_float(r[4 * j4 + 1]) + b.y);
-                        v[4 * j4 + 2] = relu_ref(__uint_as_float(r[4 * j4 + 2]) + b.z);
-                        v[4 * j4 + 3] = relu_ref(__uint_as_float(r[4 * j4 + 3]) + b.w);
+                        v[4 * j4] = relu_ref(__uint_as_float(r[c][4 * j4]) + b.x);
+                        v[4 * j4 + 1] = relu_ref(__uint_as_float(r[c][4 * j4 + 1]) + b.y);
+                        v[4 * j4 + 2] = relu_ref(__uint_as_float(r[c][4 * j4 + 2]) + b.z);
+                        v[4 * j4 + 3] = relu_ref(__uint_as_float(r[c][4 * j4 + 3]) + b.w);
                     }
                     if (!last) {
                         uint32_t t1[8], t2[8], t3[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) split3(v[2 * j], v[2 * j + 1], t1[j], t2[j], t3[j]);
-                        const uint32_t col = lane_t + A_COL + uint32_t(g0 / 2);
+                        const uint32_t col = lane_t + A_COL + out_buf * A_BUF + uint32_t(g0 / 2);
                         tmem_st8(col, t1);
                         tmem_st8(col + HH, t2);
                         tmem_st8(col + 2 * HH, t3);
@@ -199,30 +295,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         }
                     }
                 }
-                if (!last) tmem_st_wait();
-                fence_before_sync();      // this thread's tensor-memory reads / writes are done before the next layer is issued
-                __syncthreads();
+                tmem_st_wait();
+                fence_before_sync();      // this thread's tensor-memory reads and writes are done: D_grp and the K half may be reused / read
+                if (last && sub == 2 * WPG - 1) {   // before the arrival that lets the next row tile run: bar_part can never be two phases ahead
+                    mbar_wait(bar_part, ph_part);
+                    ph_part ^= 1;
+                }
+                mbar_arrive(&bar_ready[grp]);
+                t_drain += clock64() - c1;
             }
-            // ---- output: lower half adds the upper half's partial sums and stores -------------------------------------------
-            if (half == 1) s_part[m] = make_float4(y0, y1, y2, y3);
-            __syncthreads();
-            if (half == 0 && i_pt < n_slab) {
-                const float4 o = s_part[m];
-                y0 = (b2.x + y0) + o.x; y1 = (b2.y + y1) + o.y; y2 = (b2.z + y2) + o.z; y3 = (b2.w + y3) + o.w;
-                if (FIELDS) {
-                    a.sigma[s][i_pt] = y0;
-                    a.u[s][i_pt] = y1;
-                    a.u[s][n + i_pt] = y2;
-                    a.u[s][2 * n + i_pt] = y3;
-                } else {
-                    a.out_aos[i_pt] = make_float4(y0, y1, y2, y3);
+            const long long c2 = clock64();
+            // ---- outputs: the last column share of a row collects the other shares' partial sums and stores -----------------
+            float4* part = s_part + (rt & 1) * 3 * TILE;
+            if (sub != 2 * WPG - 1) {
+                part[sub * TILE + m] = make_float4(y0, y1, y2, y3);
+                mbar_arrive(bar_part);
+            } else {
+                const long long tile = blockIdx.x + (rt / NS) * gridDim.x;
+                const int sl = int(rt % NS);
+                const long long i_pt = tile * TILE + m;
+                if (i_pt < n_slab) {
+                    float4 o = b2;
+#pragma unroll
+                    for (int k = 0; k < 2 * WPG - 1; ++k) {
+                        const float4 pk = part[k * TILE + m];
+                        o.x += pk.x; o.y += pk.y; o.z += pk.z; o.w += pk.w;
+                    }
+                    y0 += o.x; y1 += o.y; y2 += o.z; y3 += o.w;
+                    if (FIELDS) {
+                        a.sigma[sl][i_pt] = y0;
+                        a.u[sl][i_pt] = y1;
+                        a.u[sl][n + i_pt] = y2;
+                        a.u[sl][2 * n + i_pt] = y3;
+                    } else {
+                        a.out_aos[i_pt] = make_float4(y0, y1, y2, y3);
+                    }
                 }
             }
+            t_out += clock64() - c2;
+        }
+        if (prof && blockIdx.x == 0 && m == 0 && sub % WPG == 0) {
+            unsigned long long* q = prof + 4 + grp * 8;
+            q[0] = (unsigned long long)(clock64() - e_begin);
+            q[1] = (unsigned long long)t_wprev; q[2] = (unsigned long long)t_l1; q[3] = (unsigned long long)t_wfull;
+            q[4] = (unsigned long long)t_drain; q[5] = (unsigned long long)t_out;
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_free<TmemCols<H>::value>(tbase);
+    if (warp == MMA_WARP) tmem_free<TmemCols<H>::value>(tbase);
 }
 
 template <int H, bool FIELDS>
@@ -231,8 +352,26 @@ int launch_t(const void* mlp_const, const DeepArgs& a, const uint8_t* wparts, in
     if (smem < MIN_SMEM) smem = MIN_SMEM;
     cudaError_t e = cudaFuncSetAttribute(k_mlp_deep_tc<H, FIELDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return int(e);
-    k_mlp_deep_tc<H, FIELDS><<<grid_blocks, TC_THREADS, smem, st>>>(*static_cast<const MlpConst<H>*>(mlp_const), a, wparts);
-    return int(cudaGetLastError());
+    // development aid: PHYSAD_DEEP_TC_PROF=1 prints block 0's cycle counters (MMA thread: total / waiting for the epilogues;
+    // thread 0 of each epilogue group: total / waiting / layer 1 / waiting for the MMAs / draining / output) after a sync
+    static const bool want_prof = getenv("PHYSAD_DEEP_TC_PROF") != nullptr;
+    static unsigned long long* d_prof = nullptr;
+    if (want_prof && !d_prof) {
+        cudaMalloc(&d_prof, 32 * sizeof(unsigned long long));
+    }
+    if (want_prof) cudaMemsetAsync(d_prof, 0, 32 * sizeof(unsigned long long), st);
+    k_mlp_deep_tc<H, FIELDS><<<grid_blocks, TcThreads<H>::value, smem, st>>>(*static_cast<const MlpConst<H>*>(mlp_const), a, wparts,
+                                                                    want_prof ? d_prof : nullptr);
+    cudaError_t le = cudaGetLastError();
+    if (want_prof && le == cudaSuccess) {
+        unsigned long long h[32];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[deep_tc H=%d L=%d] mma: total %llu wait_ready %llu row_tiles %llu | g0: total %llu wprev %llu l1 %llu wfull %llu drain %llu out %llu"
+                        " | g1: total %llu wprev %llu l1 %llu wfull %llu drain %llu out %llu\n",
+                H, a.hidden_layers, h[0], h[1], h[2], h[4], h[5], h[6], h[7], h[8], h[9], h[12], h[13], h[14], h[15], h[16], h[17]);
+    }
+    return int(le);
 }
 
 uint16_t bf16_rn(float f) {

@@ -12,6 +12,13 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
+// exactly one lane of a CONVERGED warp gets true (the compiler then knows a single lane is active: no broadcast loops)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -94,6 +101,18 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_taddr, uint32_t a_taddr, 
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_taddr),
         "r"(a_taddr), "l"(b_desc), "r"(idesc), "r"(uint32_t(accumulate))
+        : "memory");
+}
+// the same with the shared-memory descriptor as two words (the low word carries the address: advancing an operand is
+// one 32-bit add)
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_taddr, uint32_t a_taddr, uint32_t b_desc_lo, uint32_t b_desc_hi, uint32_t idesc,
+                                            bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_taddr),
+        "r"(a_taddr), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(uint32_t(accumulate))
         : "memory");
 }
 // the same with A from shared memory

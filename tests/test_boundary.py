@@ -132,6 +132,10 @@ def test_strict_kernels_have_no_contracted_fma_in_mlp(libpath):
     may_fuse = ("k_phys_grad", "k_tangent_loss")
     assert all(v["FFMA2"] == 0 for k, v in counts.items() if not any(n in k for n in may_fuse)), \
         {k: v for k, v in counts.items() if v["FFMA2"] and not any(n in k for n in may_fuse)}
+    # the tensor-core fast mode of the deep MLP (explicitly not bit-exact): its layer 1 must still be the strict one,
+    # its only FFMAs are the 4 x 16 of the unrolled output-layer chunk
+    tcs = {k: v for k, v in counts.items() if "k_mlp_deep_tc" in k}
+    assert len(tcs) == 6 and all(v["FMUL2"] >= 3 and v["FADD2"] >= v["FMUL2"] and v["FFMA"] == 64 for v in tcs.values()), tcs
     tang = {k: v for k, v in counts.items() if "k_tangent_loss" in k}
     assert len(tang) == 3 and all(v["FMUL2"] > 0 and v["FADD2"] > 0 for v in tang.values()), tang
     gradk = {k: v for k, v in counts.items() if "k_phys_grad" in k}
@@ -139,7 +143,7 @@ def test_strict_kernels_have_no_contracted_fma_in_mlp(libpath):
     fused = {k: v for k, v in counts.items() if "k_fused_mlp_phys_loss" in k}
     assert fused and all(v["FMUL"] + v.get("FMUL2", 0) > 0 for v in fused.values())
     grid = {k: v for k, v in counts.items() if "k_mlp_grid" in k or "k_mlp_forward_4x4" in k or "k_strict_gemm" in k
-            or "k_mlp_deep" in k}
+            or ("k_mlp_deep" in k and "k_mlp_deep_tc" not in k)}
     assert grid and any("k_strict_gemm" in k for k in grid) and any("k_mlp_deep" in k for k in grid), "MLP kernels not found in SASS"
     for k, v in grid.items():
         assert v["FMUL"] + v["FMUL2"] > 0 and v["FADD"] + v["FADD2"] > 0, (k, v)

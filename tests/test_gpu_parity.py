@@ -196,6 +196,76 @@ def test_deep_mlp_many_tiles_and_slabs(ctx, port, H, L, shape):
         assert f[3 + k].numel() == 3 * n
 
 
+@pytest.mark.parametrize("H,L,shape", [(128, 3, (130, 37, 11)), (128, 2, (64, 64, 5)), (64, 5, (257, 19, 9)), (64, 2, (33, 7, 3)),
+                                       (32, 3, (300, 41, 7))])
+def test_deep_fast_mode_tracks_the_strict_kernel(ctx, port, H, L, shape):
+    """Tensor-core fast mode (physad_set_deep_mode 1: three-term bf16 operands, fp32 accumulation; additive, explicitly
+    NOT bit-exact): outputs within 1e-5 of the strict kernel's (measured ~1e-6, relative to the largest output), ragged
+    last tile, several row tiles per block, z-slabs identical to the whole-grid rows, losses within 1e-4 relative."""
+    from phys_autodiff_b200 import PhysadError
+    rng = np.random.default_rng(11 * H + L)
+    og = OGrid(*shape, 1, 1, 1, 2e-3, True)
+    g = _g(og)
+    W1, b1, W2, b2 = port.mlp_random_init(H, 321, 0.25)
+    Wh = rng.uniform(-0.2, 0.2, (L - 1) * H * H).astype(np.float32)
+    bh = rng.uniform(-0.2, 0.2, (L - 1) * H).astype(np.float32)
+    ctx.set_weights_deep(_cfg(H), L, W1, b1, Wh, bh, W2, b2)
+    strict = ctx.mlp_grid_infer_deep(g, 0.3).cpu().numpy()
+    fs = ctx.mlp_generate_fields_deep(g, 0.25, 2e-3)
+    ls = ctx.phys_loss(g, _pw(), fs)
+    ctx.set_deep_mode(1)
+    try:
+        fast = ctx.mlp_grid_infer_deep(g, 0.3).cpu().numpy()
+        scale = np.abs(strict).max()
+        assert np.abs(fast - strict).max() <= 1e-5 * scale
+        assert not np.array_equal(fast, strict) or L == 1     # it really is the other arithmetic
+        again = ctx.mlp_grid_infer_deep(g, 0.3).cpu().numpy()
+        assert np.array_equal(again, fast)                     # deterministic
+        plane = og.nx * og.ny
+        z1 = max(1, og.nz // 2)
+        for z0, z1 in [(0, z1), (z1, og.nz)]:
+            part = ctx.mlp_grid_infer_deep(g, 0.3, slab=(z0, z1)).cpu().numpy()
+            assert np.array_equal(part, fast[z0 * plane: z1 * plane])
+        ff = ctx.mlp_generate_fields_deep(g, 0.25, 2e-3)
+        for x, y in zip(fs, ff):
+            assert float((x - y).abs().max()) <= 1e-5 * float(x.abs().max())
+        at_t = ctx.mlp_grid_infer_deep(g, 0.25).cpu().numpy()
+        assert np.array_equal(ff[1].cpu().numpy(), at_t[:, 0])                      # the t slice is the infer output
+        lf = ctx.phys_loss(g, _pw(), ff)
+        assert abs(lf[0] - ls[0]) <= 1e-4 * abs(ls[0]) and abs(lf[1] - ls[1]) <= 1e-4 * abs(ls[1])
+    finally:
+        ctx.set_deep_mode(0)
+    assert np.array_equal(ctx.mlp_grid_infer_deep(g, 0.3).cpu().numpy(), strict)   # back to the parity mode
+
+
+def test_deep_fast_mode_refuses_what_it_cannot_hold(ctx, port):
+    """Shapes whose layer images do not fit in shared memory (H = 128 with more than 3 hidden layers) and one-hidden-layer
+    networks return PHYSAD_E_UNSUPPORTED in mode 1 -- never a silent fall back to the other arithmetic."""
+    from phys_autodiff_b200 import PhysadError
+    rng = np.random.default_rng(5)
+    og = OGrid(16, 8, 4, 1, 1, 1, 2e-3, True)
+    g = _g(og)
+    for H, L in [(128, 4), (64, 1)]:
+        W1, b1, W2, b2 = port.mlp_random_init(H, 1, 0.25)
+        Wh = rng.uniform(-0.2, 0.2, (L - 1) * H * H).astype(np.float32)
+        bh = rng.uniform(-0.2, 0.2, (L - 1) * H).astype(np.float32)
+        ctx.set_weights_deep(_cfg(H), L, W1, b1, Wh, bh, W2, b2)
+        ctx.set_deep_mode(1)
+        try:
+            if L == 1:
+                ctx.mlp_grid_infer_deep(g, 0.3)        # one hidden layer: served by the reference-pinned kernel in every mode
+            else:
+                with pytest.raises(PhysadError, match="fast mode"):
+                    ctx.mlp_grid_infer_deep(g, 0.3)
+                with pytest.raises(PhysadError, match="fast mode"):
+                    ctx.mlp_generate_fields_deep(g, 0.25, 2e-3)
+        finally:
+            ctx.set_deep_mode(0)
+        ctx.mlp_grid_infer_deep(g, 0.3)                # the strict kernel takes every depth
+    with pytest.raises(PhysadError):
+        ctx.set_deep_mode(2)
+
+
 def test_error_paths_and_empty_inputs(ctx, checker):
     """Status codes instead of crashes: bad arguments, unsupported shapes, missing weights, empty batches."""
     import ctypes as C
