@@ -33,6 +33,15 @@ UNIT = "points/s"
 T0, DT, SEED, SCALE = 0.25, 2e-3, 777, 0.25
 
 
+def bf16_peak():
+    """Dense bf16 TFLOP/s of this pool's B200s (driver-written MEASURED_PEAKS.json, burst figure); nominal 2250 otherwise."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["bf16_tflops"])
+    except Exception:
+        return 2250.0
+
+
 def flops_per_point(H: int) -> int:
     """Algorithmic work, SURVEY.md section 8(d): 3 slices x 2*(4H + 4H) MLP flops + 3H ReLU + 60 stencil + 8 reduction."""
     return 51 * H + 68
@@ -438,9 +447,38 @@ def main():
                         ts_f.append(e0.elapsed_time(e1)); ts_p.append(e1.elapsed_time(e2))
                 fl = 3 * (2 * 4 * H2 + (L - 1) * 2 * H2 * H2 + 2 * 4 * H2) + 3 * L * H2
                 ms_f, ms_p = statistics.mean(ts_f), statistics.mean(ts_p)
-                sweep.append({"H": H2, "hidden_layers": L, "ms_fields": ms_f, "ms_phys_loss": ms_p,
-                              "value": g.N / ((ms_f + ms_p) * 1e-3), "unit": UNIT, "mlp_flops_per_point": fl,
-                              "mlp_tflops": fl * g.N / (ms_f * 1e-3) / 1e12, "frac_of_strict_fp32_peak": fl * g.N / (ms_f * 1e-3) / 1e12 / peak_strict})
+                row = {"H": H2, "hidden_layers": L, "ms_fields": ms_f, "ms_phys_loss": ms_p,
+                       "value": g.N / ((ms_f + ms_p) * 1e-3), "unit": UNIT, "mlp_flops_per_point": fl,
+                       "mlp_tflops": fl * g.N / (ms_f * 1e-3) / 1e12, "frac_of_strict_fp32_peak": fl * g.N / (ms_f * 1e-3) / 1e12 / peak_strict}
+                # the same network with its hidden -> hidden layers on the tensor cores (tcgen05, three-term bf16 operands, six
+                # term products per layer; additive and NOT bit-exact): time, the deviation from the strict fields, and the
+                # tensor-pipe rate of the 6 x 2 H^2 bf16 flops it issues per row and layer against the measured bf16 peak
+                ctx.set_deep_mode(1)
+                try:
+                    ffast = ctx.mlp_generate_fields_deep(g, T0, DT)
+                    tf = []
+                    for it in range(3):
+                        flush.zero_()
+                        e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+                        e0.record(); ctx.mlp_generate_fields_deep(g, T0, DT); e1.record(); e1.synchronize()
+                        if it:
+                            tf.append(e0.elapsed_time(e1))
+                    facc = ctx.phys_loss_acc(g, ffast)
+                    ls_, lf_ = ctx.finalize(dacc.cpu().numpy(), pw, g.N), ctx.finalize(facc.cpu().numpy(), pw, g.N)
+                    ms_fast = statistics.mean(tf)
+                    tc_fl = 3 * (L - 1) * 6 * 2 * H2 * H2
+                    row["tensor_core_fast_mode"] = {
+                        "ms_fields": ms_fast, "speedup_vs_strict": ms_f / ms_fast,
+                        "max_output_err_over_max_output": max(float((x - y).abs().max() / x.abs().max()) for x, y in zip(fields, ffast)),
+                        "loss_rel_err": [abs(float(x) - float(y)) / abs(float(x)) for x, y in zip(ls_, lf_)],
+                        "bf16_tflops_issued": tc_fl * g.N / (ms_fast * 1e-3) / 1e12,
+                        "frac_of_bf16_peak": tc_fl * g.N / (ms_fast * 1e-3) / 1e12 / bf16_peak()}
+                    del ffast
+                except Exception as e:      # shapes whose layer images do not fit in shared memory: PHYSAD_E_UNSUPPORTED
+                    row["tensor_core_fast_mode"] = {"unsupported": str(e)[:120]}
+                finally:
+                    ctx.set_deep_mode(0)
+                sweep.append(row)
                 del fields
         extra["depth_sweep"] = sweep
         ctx.set_weights(cfg, *w)

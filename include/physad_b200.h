@@ -135,9 +135,10 @@ int physad_set_weights_deep(physad_ctx* ctx, const physad_mlp_config* cfg, int h
  *   0: strict fp32 on the CUDA cores -- bit-identical to the CPU restatement (the parity mode);
  *   1: tcgen05 tensor cores, every fp32 operand split into three bf16 terms, six term products accumulated in fp32
  *      (deep_tc_kernels.cuh): NOT bit-exact -- outputs agree with mode 0 to ~1e-6 relative, the error class of an
- *      FFMA-contracted evaluation such as the reference's own CUDA kernels (src/mlp_cuda.cu).  Needs hidden_layers >= 2 and
- *      all layer images resident in shared memory (H = 128: <= 3 hidden layers; H = 64: <= 9; H = 32: <= 16); other
- *      shapes return PHYSAD_E_UNSUPPORTED from the deep calls while mode 1 is selected.  Layer 1 stays strict. */
+ *      FFMA-contracted evaluation such as the reference's own CUDA kernels (src/mlp_cuda.cu).  Needs hidden_layers >= 2
+ *      (with one hidden layer there is no hidden -> hidden contraction: PHYSAD_E_UNSUPPORTED from the forced deep kernel;
+ *      the default route for one hidden layer is the reference-pinned kernel in either mode).  Layer images stay resident
+ *      in shared memory when they fit (H = 128: <= 3 hidden layers), else they are streamed from L2.  Layer 1 stays strict. */
 int physad_set_deep_mode(physad_ctx* ctx, int mode);
 /* Stage-wise evaluation over the grid (coordinates from the index); outputs as the one-layer calls above. */
 int physad_mlp_grid_infer_deep_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float* out,

@@ -605,8 +605,8 @@ int launch_deep(physad_ctx* c, const physad_grid* g, const physad_slab& s, const
     fill_const<H>(c, tc, k);
     if (c->deep_mode == 1) {
         if (!deep_tc_supported(H, c->deep_layers) || !c->deep_tc_ok)
-            return fail(PHYSAD_E_UNSUPPORTED, "deep fast mode: needs >= 2 hidden layers whose operand images fit in shared memory "
-                                              "(H = 128: <= 3 hidden layers, H = 64: <= 9)");
+            return fail(PHYSAD_E_UNSUPPORTED, "deep fast mode: needs at least 2 hidden layers (the tensor cores only take the "
+                                              "hidden -> hidden contractions)");
         CU(cudaError_t(deep_tc_launch(H, FIELDS, &k, a, c->d_wparts, c->sm_count, st)));
         c->launches++;
         return 0;

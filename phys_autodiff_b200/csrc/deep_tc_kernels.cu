@@ -49,10 +49,16 @@ constexpr size_t MIN_SMEM = 120 * 1024;         // more than half an SM's shared
 template <int H>
 struct TmemCols { static constexpr uint32_t value = H == 128 ? 512u : (H == 64 ? 256u : 128u); };   // = H + 2 * 3 H/2
 
+constexpr size_t SMEM_CAP = 227 * 1024;
+
+// nbuf layer images + the small tables of an nl-layer network
 template <int H>
-size_t smem_for(int nl) {
-    return size_t(nl) * 3 * H * H * 2 + 20 * H + 16 * H + size_t(nl) * H * 4 + 2 * 3 * TILE * 16 + 64;
+size_t smem_for(int nl, int nbuf) {
+    return size_t(nbuf) * 3 * H * H * 2 + 20 * H + 16 * H + size_t(nl) * H * 4 + 2 * 3 * TILE * 16 + 96;
 }
+// all layers resident if they fit, else two buffers that the MMA warp refills one layer ahead
+template <int H>
+int weight_buffers(int nl) { return smem_for<H>(nl, nl) <= SMEM_CAP ? nl : 2; }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -61,7 +67,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int H, bool FIELDS>
 __global__ void __launch_bounds__(TcThreads<H>::value, 1)
     k_mlp_deep_tc(const __grid_constant__ MlpConst<H> w, const __grid_constant__ DeepArgs a, const uint8_t* __restrict__ wparts,
-                  unsigned long long* __restrict__ prof) {
+                  const int nbuf, unsigned long long* __restrict__ prof) {
     constexpr int NS = FIELDS ? 3 : 1;
     constexpr int HH = H / 2;                    // hidden units / accumulator columns per group; columns of one A term
     constexpr uint32_t D_COL = 0, A_COL = H, A_BUF = 3 * HH;   // A operand b, term p: columns A_COL + b A_BUF + p HH ...
@@ -74,7 +80,8 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
     static_assert(CPT % 16 == 0, "an epilogue thread drains whole 16-column chunks");
     extern __shared__ __align__(128) uint8_t smem[];
     const int nl = a.hidden_layers - 1;
-    const size_t w_bytes = size_t(nl) * 3 * TERM_BYTES;
+    const size_t w_bytes = size_t(nbuf) * 3 * TERM_BYTES;
+    const bool resident = nbuf >= nl;            // else: layer of step s lives in buffer s & 1
     float2* s_l1 = reinterpret_cast<float2*>(smem + w_bytes);                      // [5][H/2], as deep_kernels.cu
     float4* s_w2 = reinterpret_cast<float4*>(smem + w_bytes + 20 * H);             // {W2[0..3, h]}
     float* s_bh = reinterpret_cast<float*>(smem + w_bytes + 36 * H);               // [nl][H]
@@ -84,7 +91,8 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
     uint64_t* bar_full = bars + 1;               // [2] D_n complete (tcgen05.commit)
     uint64_t* bar_ready = bars + 3;              // [2] group g: K half g of the next A operand written, D_g drained
     uint64_t* bar_part = bars + 5;               // the other threads' partial outputs of a row are in s_part
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* bar_wbuf = bars + 6;               // [2] streaming: the layer image in buffer b has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, m = tid & (TILE - 1);
     const int sub = tid >> 7;                    // which CPT columns of the hidden width (2 WPG = the MMA warp)
@@ -96,6 +104,8 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
         mbar_init(&bar_ready[0], TILE * WPG);
         mbar_init(&bar_ready[1], TILE * WPG);
         mbar_init(bar_part, TILE * (2 * WPG - 1));
+        mbar_init(&bar_wbuf[0], 1);
+        mbar_init(&bar_wbuf[1], 1);
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc<TmemCols<H>::value>(tmem_slot);
@@ -115,7 +125,7 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (tid == 0) {
+    if (tid == 0 && resident) {
         mbar_expect_tx(bar_w, uint32_t(w_bytes));
         for (int i = 0; i < nl * 3; ++i) bulk_g2s(smem + size_t(i) * TERM_BYTES, wparts + size_t(i) * TERM_BYTES, TERM_BYTES, bar_w);
     }
@@ -129,7 +139,25 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
     if (warp == MMA_WARP) {
         // ================= MMA warp: lane 0 issues, in layer order; `step` counts layers over all row tiles =================
         {
-            mbar_wait(bar_w, 0);
+            const long long total_steps = my_rts * nl;
+            // streaming: the image of step s's layer goes to buffer s & 1 (one elected lane issues, everybody waits)
+            auto stream_layer = [&](long long s_) {
+                if (elect_one()) {
+                    uint64_t* bar = &bar_wbuf[s_ & 1];
+                    const uint8_t* src = wparts + size_t(s_ % nl) * 3 * TERM_BYTES;
+                    uint8_t* dst = smem + size_t(s_ & 1) * 3 * TERM_BYTES;
+                    mbar_expect_tx(bar, 3 * TERM_BYTES);
+                    for (int i = 0; i < 3; ++i) bulk_g2s(dst + size_t(i) * TERM_BYTES, src + size_t(i) * TERM_BYTES, TERM_BYTES, bar);
+                }
+                __syncwarp();
+            };
+            uint32_t ph_w[2] = {0, 0};
+            if (resident) {
+                mbar_wait(bar_w, 0);
+            } else {
+                if (total_steps > 0) stream_layer(0);
+                if (total_steps > 1) stream_layer(1);
+            }
             const uint32_t idesc = idesc_bf16_f32(TILE, HH);
             const uint32_t w0 = smem_u32(smem);
             // t3(a) t1(W), t2 t2, t1 t3, t2 t1, t1 t2, t1 t1: ascending magnitude
@@ -142,7 +170,11 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
 #pragma unroll 1
                 for (int l = 0; l < nl; ++l, ++step) {
                     const uint32_t a_in = tbase + A_COL + uint32_t(step & 1) * A_BUF;
-                    const uint32_t wl = w0 + uint32_t(l) * 3 * TERM_BYTES;
+                    const uint32_t wl = w0 + uint32_t(resident ? l : int(step & 1)) * 3 * TERM_BYTES;
+                    if (!resident) {
+                        mbar_wait(&bar_wbuf[step & 1], ph_w[step & 1]);
+                        ph_w[step & 1] ^= 1;
+                    }
                     const uint32_t b_lo = (wl >> 4) | ((LBO >> 4) << 16), b_hi = (SBO >> 4) | (1u << 14);   // smem_desc(), in two words
 #pragma unroll
                     for (int nh = 0; nh < 2; ++nh) {
@@ -155,6 +187,9 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
                                 t_wait += clock64() - t0;
                                 ph_ready[kh] ^= 1;
                                 fence_after_sync();
+                                // group 1 has drained the previous layer, so every MMA of that layer has completed and
+                                // its buffer may be overwritten: fetch the NEXT layer's image into it, 3/4 of a layer ahead
+                                if (!resident && kh == 1 && step >= 1 && step + 1 < total_steps) stream_layer(step + 1);
                             }
                             if (elect_one()) {
 #pragma unroll
@@ -348,7 +383,8 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
 
 template <int H, bool FIELDS>
 int launch_t(const void* mlp_const, const DeepArgs& a, const uint8_t* wparts, int grid_blocks, cudaStream_t st) {
-    size_t smem = smem_for<H>(a.hidden_layers - 1);
+    const int nl = a.hidden_layers - 1, nbuf = weight_buffers<H>(nl);
+    size_t smem = smem_for<H>(nl, nbuf);
     if (smem < MIN_SMEM) smem = MIN_SMEM;
     cudaError_t e = cudaFuncSetAttribute(k_mlp_deep_tc<H, FIELDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return int(e);
@@ -360,8 +396,8 @@ int launch_t(const void* mlp_const, const DeepArgs& a, const uint8_t* wparts, in
         cudaMalloc(&d_prof, 32 * sizeof(unsigned long long));
     }
     if (want_prof) cudaMemsetAsync(d_prof, 0, 32 * sizeof(unsigned long long), st);
-    k_mlp_deep_tc<H, FIELDS><<<grid_blocks, TcThreads<H>::value, smem, st>>>(*static_cast<const MlpConst<H>*>(mlp_const), a, wparts,
-                                                                    want_prof ? d_prof : nullptr);
+    k_mlp_deep_tc<H, FIELDS><<<grid_blocks, TcThreads<H>::value, smem, st>>>(*static_cast<const MlpConst<H>*>(mlp_const), a, wparts, nbuf,
+                                                                             want_prof ? d_prof : nullptr);
     cudaError_t le = cudaGetLastError();
     if (want_prof && le == cudaSuccess) {
         unsigned long long h[32];
@@ -391,13 +427,12 @@ float bf16_to_float(uint16_t b) {
 }  // namespace
 
 bool deep_tc_supported(int H, int hidden_layers) {
-    if (hidden_layers < 2) return false;
+    if (hidden_layers < 2 || hidden_layers > 16) return false;
     const int nl = hidden_layers - 1;
-    const size_t cap = 227 * 1024;
     switch (H) {
-        case 32: return smem_for<32>(nl) <= cap;
-        case 64: return smem_for<64>(nl) <= cap;
-        case 128: return smem_for<128>(nl) <= cap;
+        case 32: return smem_for<32>(nl, weight_buffers<32>(nl)) <= SMEM_CAP;
+        case 64: return smem_for<64>(nl, weight_buffers<64>(nl)) <= SMEM_CAP;
+        case 128: return smem_for<128>(nl, weight_buffers<128>(nl)) <= SMEM_CAP;
     }
     return false;
 }

@@ -25,7 +25,9 @@ namespace physad {
 inline size_t deep_tc_layer_bytes(int H) { return size_t(3) * H * H * 2; }
 // W: the layer's [H out][H in] row-major fp32 weights (the reference's W2-style layout).  Host function.
 void deep_tc_pack_layer(int H, const float* W, uint8_t* image);
-// Whether (H, hidden_layers) fits: H in {32, 64, 128}, 2 <= hidden_layers, and all layer images resident in shared memory.
+// Whether (H, hidden_layers) is built: H in {32, 64, 128}, 2 <= hidden_layers <= 16.  All layer images stay resident in
+// shared memory when they fit (H = 128: <= 3 hidden layers, H = 64: <= 10); otherwise two buffers are refilled from L2 one
+// layer ahead (96 KB per layer and 128 rows at H = 128 -- that mode is L2-bandwidth-bound, not tensor-pipe-bound).
 bool deep_tc_supported(int H, int hidden_layers);
 // `a.wh` is ignored; `wparts` = device pointer to (hidden_layers - 1) consecutive layer images; a.bh as in deep_launch.
 int deep_tc_launch(int H, bool fields, const void* mlp_const, const DeepArgs& a, const uint8_t* wparts, int grid_blocks, cudaStream_t st);
