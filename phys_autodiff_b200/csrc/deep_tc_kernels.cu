@@ -36,6 +36,12 @@ namespace {
 
 using namespace tc;
 
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 constexpr int TILE = 128;                       // rows of one MMA
 // epilogue warps per (group, lane quarter): each takes 1/WPG of the group's columns.  Two for H >= 64: the epilogues are
 // latency-bound with one (measured: tensor pipe waiting 25 % of the time), a thread's share must stay a multiple of 16.
@@ -54,7 +60,7 @@ constexpr size_t SMEM_CAP = 227 * 1024;
 // nbuf layer images + the small tables of an nl-layer network
 template <int H>
 size_t smem_for(int nl, int nbuf) {
-    return size_t(nbuf) * 3 * H * H * 2 + 20 * H + 16 * H + size_t(nl) * H * 4 + 2 * 3 * TILE * 16 + 96;
+    return size_t(nbuf) * 3 * H * H * 2 + 28 * H + 16 * H + size_t(nl) * H * 4 + 2 * 3 * TILE * 16 + 96;
 }
 // all layers resident if they fit, else two buffers that the MMA warp refills one layer ahead
 template <int H>
@@ -82,10 +88,11 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
     const int nl = a.hidden_layers - 1;
     const size_t w_bytes = size_t(nbuf) * 3 * TERM_BYTES;
     const bool resident = nbuf >= nl;            // else: layer of step s lives in buffer s & 1
-    float2* s_l1 = reinterpret_cast<float2*>(smem + w_bytes);                      // [5][H/2], as deep_kernels.cu
-    float4* s_w2 = reinterpret_cast<float4*>(smem + w_bytes + 20 * H);             // {W2[0..3, h]}
-    float* s_bh = reinterpret_cast<float*>(smem + w_bytes + 36 * H);               // [nl][H]
-    float4* s_part = reinterpret_cast<float4*>(smem + w_bytes + 36 * H + size_t(nl) * H * 4);   // [2][3][TILE] partial outputs
+    // layer-1 pairs [7][H/2]: 0..2 W1[., 0..2] half-swapped | 3 b1 | 4..6 fl(W1[., 3] t_s) for the three slices
+    float2* s_l1 = reinterpret_cast<float2*>(smem + w_bytes);
+    float4* s_w2 = reinterpret_cast<float4*>(smem + w_bytes + 28 * H);             // {W2[0..3, h]}
+    float* s_bh = reinterpret_cast<float*>(smem + w_bytes + 44 * H);               // [nl][H]
+    float4* s_part = reinterpret_cast<float4*>(smem + w_bytes + 44 * H + size_t(nl) * H * 4);   // [2][3][TILE] partial outputs
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 3 * TILE);
     uint64_t* bar_w = bars;                      // weights landed
     uint64_t* bar_full = bars + 1;               // [2] D_n complete (tcgen05.commit)
@@ -111,11 +118,13 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
     if (warp == MMA_WARP) tmem_alloc<TmemCols<H>::value>(tmem_slot);
     for (int q = tid; q < H / 2; q += TC_THREADS) {
         const float4 ra = __ldg(reinterpret_cast<const float4*>(a.W1) + 2 * q), rb = __ldg(reinterpret_cast<const float4*>(a.W1) + 2 * q + 1);
-        s_l1[q] = make_float2(__ldg(a.b1 + 2 * q), __ldg(a.b1 + 2 * q + 1));
-        s_l1[H / 2 + q] = make_float2(rb.x, ra.x);        // half-swapped for mul2_rn / add2_rn_swapped (mlp_eval.cuh)
-        s_l1[2 * (H / 2) + q] = make_float2(rb.y, ra.y);
-        s_l1[3 * (H / 2) + q] = make_float2(rb.z, ra.z);
-        s_l1[4 * (H / 2) + q] = make_float2(ra.w, rb.w);
+        s_l1[q] = make_float2(rb.x, ra.x);                // half-swapped for mul2_rn / add2_rn_swapped (mlp_eval.cuh)
+        s_l1[H / 2 + q] = make_float2(rb.y, ra.y);
+        s_l1[2 * (H / 2) + q] = make_float2(rb.z, ra.z);
+        s_l1[3 * (H / 2) + q] = make_float2(__ldg(a.b1 + 2 * q), __ldg(a.b1 + 2 * q + 1));
+#pragma unroll
+        for (int sl = 0; sl < 3; ++sl)                    // fl(W1[.,3] t_s): the product the strict path rounds once per slice
+            s_l1[(4 + sl) * (H / 2) + q] = make_float2(__fmul_rn(ra.w, a.tc[sl]), __fmul_rn(rb.w, a.tc[sl]));
     }
     for (int h = tid; h < H; h += TC_THREADS) {
         const float4 v = w.w2[h];                          // {W2[1,h], W2[0,h], W2[3,h], W2[2,h]}
@@ -233,7 +242,8 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
             const int zl = int(p / plane), rem = int(p - (long long)zl * plane);
             const int y = rem / a.nx, x = rem - y * a.nx;
             const float cx = __ldg(a.cxs + x), cy = __ldg(a.cys + y), cz = __ldg(a.czs + a.z_begin + zl);
-            const float tcs = FIELDS ? a.tc[sl] : a.tc[1];
+            const float2* bt = s_l1 + (4 + (FIELDS ? sl : 1)) * (H / 2);
+            const f32x2 cx2 = bcast2(cx), cy2 = bcast2(cy), cz2 = bcast2(cz);
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 uint32_t t1[8], t2[8], t3[8];
@@ -241,15 +251,14 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int q = q0 + j;
-                    const float2 b1p = s_l1[q], w0s = s_l1[H / 2 + q], w1s = s_l1[2 * (H / 2) + q], w2s = s_l1[3 * (H / 2) + q];
-                    const float2 w3 = s_l1[4 * (H / 2) + q];
-                    const float2 pt = make_float2(__fmul_rn(w3.x, tcs), __fmul_rn(w3.y, tcs));
-                    const f32x2 sx = add2_rn_swapped(pack2(b1p), mul2_rn(pack2(w0s), bcast2(cx)));
-                    const f32x2 sxy = add2_rn_swapped(sx, mul2_rn(pack2(w1s), bcast2(cy)));
-                    const f32x2 sxyz = add2_rn_swapped(sxy, mul2_rn(pack2(w2s), bcast2(cz)));
-                    float v0, v1;
-                    unpack2(add2_rn(sxyz, pack2(pt)), v0, v1);
-                    split3(relu_ref(v0), relu_ref(v1), t1[j], t2[j], t3[j]);
+                    // the strict path's roundings: (((b1 + W1[.,0] x) + W1[.,1] y) + W1[.,2] z) + fl(W1[.,3] t), products rounded
+                    // separately (fed half-swapped so that ptxas cannot contract them, mlp_eval.cuh).  Measured against an fp64
+                    // evaluation (tools/deep_tc_truth.py): with fused multiply-adds here the loss error grows from <= 7e-6 to ~1e-5.
+                    f32x2 z2 = add2_rn_swapped(pack2(s_l1[3 * (H / 2) + q]), mul2_rn(pack2(s_l1[q]), cx2));
+                    z2 = add2_rn_swapped(z2, mul2_rn(pack2(s_l1[H / 2 + q]), cy2));
+                    z2 = add2_rn_swapped(z2, mul2_rn(pack2(s_l1[2 * (H / 2) + q]), cz2));
+                    z2 = add2_rn(z2, pack2(bt[q]));
+                    split3_relu(z2, t1[j], t2[j], t3[j]);
                 }
                 const uint32_t col = lane_t + A_COL + buf * A_BUF + uint32_t(q0);
                 tmem_st8(col, t1);
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
         };
         uint32_t ph_full = 0, ph_part = 0, ph_prev = 0;
         long long step = 0;
-        long long t_l1 = 0, t_wfull = 0, t_drain = 0, t_out = 0, t_wprev = 0;
+        long long t_l1 = 0, t_wfull = 0, t_drain = 0, t_out = 0, t_wprev = 0, t_ld = 0, t_math = 0, t_stw = 0;
         const long long e_begin = clock64();
         if (my_rts > 0) {
             layer1(0, 0);
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
             mbar_arrive(&bar_ready[grp]);
         }
         for (long long rt = 0; rt < my_rts; ++rt) {
-            float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+            f32x2 y01 = pack2(0.f, 0.f), y23 = pack2(0.f, 0.f);   // this thread's share of the four outputs
 #pragma unroll 1
             for (int l = 0; l < nl; ++l, ++step) {
                 const bool last = l == nl - 1;
@@ -298,39 +307,45 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) tmem_ld16(lane_t + D_COL + uint32_t(sub * CPT + c * 16), r[c]);
                 tmem_ld_wait();
+                const long long c_ld = clock64();
+                t_ld += c_ld - c1;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const int g0 = sub * CPT + c * 16;
-                    float v[16];
                     const float4* bp = reinterpret_cast<const float4*>(s_bh + l * H + g0);
+                    f32x2 v2[8];              // accumulator + bias, two columns per register pair
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
                         const float4 b = bp[j4];
-                        v[4 * j4] = relu_ref(__uint_as_float(r[c][4 * j4]) + b.x);
-                        v[4 * j4 + 1] = relu_ref(__uint_as_float(r[c][4 * j4 + 1]) + b.y);
-                        v[4 * j4 + 2] = relu_ref(__uint_as_float(r[c][4 * j4 + 2]) + b.z);
-                        v[4 * j4 + 3] = relu_ref(__uint_as_float(r[c][4 * j4 + 3]) + b.w);
+                        v2[2 * j4] = add2_rn(pack2(__uint_as_float(r[c][4 * j4]), __uint_as_float(r[c][4 * j4 + 1])), pack2(b.x, b.y));
+                        v2[2 * j4 + 1] = add2_rn(pack2(__uint_as_float(r[c][4 * j4 + 2]), __uint_as_float(r[c][4 * j4 + 3])), pack2(b.z, b.w));
                     }
                     if (!last) {
                         uint32_t t1[8], t2[8], t3[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) split3(v[2 * j], v[2 * j + 1], t1[j], t2[j], t3[j]);
+                        for (int j = 0; j < 8; ++j) split3_relu(v2[j], t1[j], t2[j], t3[j]);
                         const uint32_t col = lane_t + A_COL + out_buf * A_BUF + uint32_t(g0 / 2);
                         tmem_st8(col, t1);
                         tmem_st8(col + HH, t2);
                         tmem_st8(col + 2 * HH, t3);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float4 o = s_w2[g0 + j];
-                            y0 = fmaf(o.x, v[j], y0);
-                            y1 = fmaf(o.y, v[j], y1);
-                            y2 = fmaf(o.z, v[j], y2);
-                            y3 = fmaf(o.w, v[j], y3);
+                        for (int j = 0; j < 8; ++j) {
+                            float va, vb;
+                            unpack2(v2[j], va, vb);
+                            const float4 oa = s_w2[g0 + 2 * j], ob = s_w2[g0 + 2 * j + 1];
+                            const f32x2 aa = bcast2(relu_ref(va)), ab = bcast2(relu_ref(vb));
+                            y01 = fma2(pack2(oa.x, oa.y), aa, y01);
+                            y23 = fma2(pack2(oa.z, oa.w), aa, y23);
+                            y01 = fma2(pack2(ob.x, ob.y), ab, y01);
+                            y23 = fma2(pack2(ob.z, ob.w), ab, y23);
                         }
                     }
                 }
+                const long long c_st = clock64();
+                t_math += c_st - c_ld;
                 tmem_st_wait();
+                t_stw += clock64() - c_st;
                 fence_before_sync();      // this thread's tensor-memory reads and writes are done: D_grp and the K half may be reused / read
                 if (last && sub == 2 * WPG - 1) {   // before the arrival that lets the next row tile run: bar_part can never be two phases ahead
                     mbar_wait(bar_part, ph_part);
@@ -342,6 +357,9 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
             const long long c2 = clock64();
             // ---- outputs: the last column share of a row collects the other shares' partial sums and stores -----------------
             float4* part = s_part + (rt & 1) * 3 * TILE;
+            float y0, y1, y2, y3;
+            unpack2(y01, y0, y1);
+            unpack2(y23, y2, y3);
             if (sub != 2 * WPG - 1) {
                 part[sub * TILE + m] = make_float4(y0, y1, y2, y3);
                 mbar_arrive(bar_part);
@@ -374,6 +392,7 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
             q[0] = (unsigned long long)(clock64() - e_begin);
             q[1] = (unsigned long long)t_wprev; q[2] = (unsigned long long)t_l1; q[3] = (unsigned long long)t_wfull;
             q[4] = (unsigned long long)t_drain; q[5] = (unsigned long long)t_out;
+            if (grp == 0) { prof[24] = (unsigned long long)t_ld; prof[25] = (unsigned long long)t_math; prof[26] = (unsigned long long)t_stw; }
         }
     }
     fence_before_sync();
@@ -404,8 +423,8 @@ int launch_t(const void* mlp_const, const DeepArgs& a, const uint8_t* wparts, in
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[deep_tc H=%d L=%d] mma: total %llu wait_ready %llu row_tiles %llu | g0: total %llu wprev %llu l1 %llu wfull %llu drain %llu out %llu"
-                        " | g1: total %llu wprev %llu l1 %llu wfull %llu drain %llu out %llu\n",
-                H, a.hidden_layers, h[0], h[1], h[2], h[4], h[5], h[6], h[7], h[8], h[9], h[12], h[13], h[14], h[15], h[16], h[17]);
+                        " | g1: total %llu wprev %llu l1 %llu wfull %llu drain %llu out %llu | g0 drain = ld %llu + math %llu + st_wait %llu + rest\n",
+                H, a.hidden_layers, h[0], h[1], h[2], h[4], h[5], h[6], h[7], h[8], h[9], h[12], h[13], h[14], h[15], h[16], h[17], h[24], h[25], h[26]);
     }
     return int(le);
 }

@@ -40,8 +40,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol error becomes a trap (a CUDA error on the host), never a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
         if (spin > (1u << 24)) __trap();
+#ifdef PHYSAD_TC_BACKOFF_NS
+        __nanosleep(PHYSAD_TC_BACKOFF_NS);
+#endif
+    }
 }
 
 // ---- bulk copy global -> shared, completion counted in bytes on an mbarrier ----------------------------------------
@@ -130,19 +134,41 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ---- fp32 -> three bf16 terms ------------------------------------------------------------------------------------
-// v = t1 + t2 + t3 up to ~2^-24 |v|: each term is the round-to-nearest bf16 of what the previous ones left (the
-// remainders are exact in fp32).  Two values at a time: the packed word holds `lo` in bits 0..15, `hi` in 16..31.
-__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+// relu(v) = t1 + t2 + t3 EXACTLY: each term is the bf16 TRUNCATION of what the previous ones left (8 significant bits
+// each, the remainders are exact in fp32 and stay non-negative), and `.relu` turns a negative input into three zero terms
+// (t1 = 0 leaves the negative remainder, which the next conversion clamps again) -- the ReLU costs no instruction.
+// Two values at a time as an f32x2 register pair: the packed result holds the low half's term in bits 0..15.
+typedef unsigned long long f32pair;
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {   // round to nearest (tools/tc_probe.cu)
     uint32_t d;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
-__device__ __forceinline__ void split3(float lo, float hi, uint32_t& t1, uint32_t& t2, uint32_t& t3) {
-    t1 = cvt_bf16x2(lo, hi);
-    const float rl = lo - __uint_as_float(t1 << 16), rh = hi - __uint_as_float(t1 & 0xffff0000u);
-    t2 = cvt_bf16x2(rl, rh);
-    const float sl = rl - __uint_as_float(t2 << 16), sh = rh - __uint_as_float(t2 & 0xffff0000u);
-    t3 = cvt_bf16x2(sl, sh);
+__device__ __forceinline__ uint32_t cvt_rz_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ f32pair sub2(f32pair a, f32pair b) {
+    f32pair r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32pair widen_bf16x2(uint32_t t) {   // the two bf16 halves as two floats
+    f32pair r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(t << 16), "r"(t & 0xffff0000u));
+    return r;
+}
+__device__ __forceinline__ void split3_relu(f32pair v, uint32_t& t1, uint32_t& t2, uint32_t& t3) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    t1 = cvt_rz_relu_bf16x2(lo, hi);
+    const f32pair r = sub2(v, widen_bf16x2(t1));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+    t2 = cvt_rz_relu_bf16x2(lo, hi);
+    const f32pair q = sub2(r, widen_bf16x2(t2));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(q));
+    t3 = cvt_rz_relu_bf16x2(lo, hi);
 }
 
 }  // namespace tc
