@@ -31,6 +31,18 @@ void mlp_phys_loss_fused_cuda(const GridSpec& g, const MLPGridConfig& cfg, const
 void mlp_phys_loss_tangent_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, const PhysWeights& pw, float t,
                                 float* out_loss_sigma, float* out_loss_u);
 
+// Deeper networks (BASELINE config 5's depth sweep; additive -- the reference API has exactly one hidden layer,
+// include/mlp.h:5-6): 4 -> H -> ... -> H -> 4 with hidden_layers >= 1 layers of width H in {32, 64, 128}, every layer the
+// reference's layer rule (src/mlp_cpu.cpp:19-24).  Wh: (hidden_layers - 1) matrices [H x H] row-major [out][in]; bh:
+// (hidden_layers - 1) x H.  tensor_cores = false: strict fp32, bit-identical to the CPU restatement of the rule;
+// true: hidden -> hidden layers on tcgen05 with three-term bf16 operands (~1e-6 of the strict outputs, not bit-exact).
+struct DeepMLPWeights {
+    int hidden_layers = 1;
+    std::vector<float> W1, b1, Wh, bh, W2, b2;
+};
+void mlp_phys_loss_deep_cuda(const GridSpec& g, const MLPGridConfig& cfg, const DeepMLPWeights& w, const PhysWeights& pw, float t,
+                             float dt, float* out_loss_sigma, float* out_loss_u, bool tensor_cores = false);
+
 // The closed loop the reference plans in REQUIREMENT.md:155-169 ("MLP backward: pass dL/dsigma, dL/du to the MLP
 // weights") and stops short of (cpu_phys_loss_backward returns dL/dR only): the two losses of the MLP-generated
 // fields AND d(L_sigma + L_u)/d(weights), the loss VJP carried through the transposed stencil and the MLP on the

@@ -146,6 +146,11 @@ int physad_mlp_grid_infer_deep_dev(physad_ctx* ctx, const physad_grid* g, const 
 int physad_mlp_generate_fields_deep_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float dt,
                                         float* sigma_tm1, float* sigma_t, float* sigma_tp1, float* u_tm1, float* u_t,
                                         float* u_tp1, void* stream);
+/* One call for the depth sweep: the deep network's six fields (context scratch, 48 B per point) -> the residual loss of
+ * src/phys_cpu.cpp:112-149 -> the two losses on the host.  Stage-wise inside (the MLP is 50-700x the stencil's time at these
+ * depths, so fusing them would save < 3 %); the arithmetic follows physad_set_deep_mode. */
+int physad_deep_loss_host(physad_ctx* ctx, const physad_grid* g, const physad_phys_weights* w, float t, float dt,
+                          float* loss_sigma, float* loss_u);
 
 /* ---- physics operators on supplied fields (whole grid, single device) -------------------- */
 /* Residuals.  Replaces cuda_phys_residuals_fused / _nonfused (include/phys.h:67-77,120-130).

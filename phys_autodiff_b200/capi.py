@@ -83,7 +83,7 @@ EXPORTS = [
     "physad_ctx_create", "physad_ctx_destroy", "physad_ctx_sm_count", "physad_set_weights",
     "physad_mlp_forward_dev", "physad_mlp_forward_host", "physad_mlp_backward_dev", "physad_mlp_backward_host",
     "physad_mlp_grid_infer_dev", "physad_mlp_grid_infer_host",
-    "physad_set_weights_deep", "physad_set_deep_mode", "physad_mlp_grid_infer_deep_dev", "physad_mlp_generate_fields_deep_dev",
+    "physad_set_weights_deep", "physad_set_deep_mode", "physad_mlp_grid_infer_deep_dev", "physad_mlp_generate_fields_deep_dev", "physad_deep_loss_host",
     "physad_mlp_generate_fields_dev", "physad_mlp_generate_fields_host",
     "physad_phys_residuals_dev", "physad_phys_residuals_host",
     "physad_phys_loss_dev", "physad_phys_loss_host", "physad_phys_loss_slab_dev",

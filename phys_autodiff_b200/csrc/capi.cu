@@ -1049,6 +1049,27 @@ int physad_mlp_generate_fields_deep_dev(physad_ctx* c, const physad_grid* g, con
     }
 }
 
+// one call: deep network -> six fields in context scratch -> residual loss -> the two losses on the host
+int physad_deep_loss_host(physad_ctx* c, const physad_grid* g, const physad_phys_weights* w, float t, float dt, float* loss_sigma,
+                          float* loss_u) {
+    if (!c || !w) return fail(PHYSAD_E_INVALID, "deep_loss: null argument");
+    if (int rc = check_grid(g)) return rc;
+    if (int rc = deep_ready(c, "deep_loss")) return rc;
+    DeviceGuard dg(c->device);
+    const size_t N = size_t(g->nx) * g->ny * g->nz;
+    if (int rc = ensure_scratch(c, 12 * N * sizeof(float))) return rc;
+    float* f = reinterpret_cast<float*>(c->scratch);   // sigma_{-,0,+} (N each) | u_{-,0,+} (3N each)
+    if (int rc = physad_mlp_generate_fields_deep_dev(c, g, nullptr, t, dt, f, f + N, f + 2 * N, f + 3 * N, f + 6 * N, f + 9 * N, c->stream))
+        return rc;
+    if (int rc = physad_phys_loss_dev(c, g, f, f + N, f + 2 * N, f + 3 * N, f + 6 * N, f + 9 * N, c->d_acc, nullptr, nullptr, nullptr,
+                                      nullptr, c->stream))
+        return rc;
+    CU(cudaMemcpyAsync(c->h_acc, c->d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    physad_finalize_loss(c->h_acc, w, N, loss_sigma, loss_u);
+    return 0;
+}
+
 // ---- physics on supplied fields ------------------------------------------------------------------
 int physad_phys_residuals_dev(physad_ctx* c, const physad_grid* g, const float* s_m, const float* s_0, const float* s_p,
                               const float* u_m, const float* u_0, const float* u_p, float* Rs, float* Rx, float* Ry,

@@ -281,6 +281,21 @@ void mlp_phys_loss_tangent_cuda(const GridSpec& g, const MLPGridConfig& cfg, con
         die("mlp_phys_loss_tangent_cuda", rc);
 }
 
+void mlp_phys_loss_deep_cuda(const GridSpec& g, const MLPGridConfig& cfg, const DeepMLPWeights& w, const PhysWeights& pw, float t,
+                             float dt, float* out_loss_sigma, float* out_loss_u, bool tensor_cores) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const physad_grid cg = to_c(g);
+    const physad_phys_weights cw = to_c(pw);
+    const physad_mlp_config mc{int(cfg.dims.In), int(cfg.dims.H), int(cfg.dims.Out), norm_of(cfg.norm)};
+    physad_ctx* c = ctx();
+    int rc = physad_set_weights_deep(c, &mc, w.hidden_layers, w.W1.data(), w.b1.data(), w.Wh.empty() ? nullptr : w.Wh.data(),
+                                     w.bh.empty() ? nullptr : w.bh.data(), w.W2.data(), w.b2.data());
+    if (!rc) rc = physad_set_deep_mode(c, tensor_cores ? 1 : 0);
+    if (!rc) rc = physad_deep_loss_host(c, &cg, &cw, t, dt, out_loss_sigma, out_loss_u);
+    physad_set_deep_mode(c, 0);
+    if (rc) die("mlp_phys_loss_deep_cuda", rc);
+}
+
 void mlp_phys_loss_grad_cuda(const GridSpec& g, const MLPGridConfig& cfg, const MLPWeights& w, const PhysWeights& pw,
                              float t, float dt, float* out_loss_sigma, float* out_loss_u, MLPWeights& grad) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -211,6 +211,14 @@ class Context:
               "set_weights_deep")
         self.cfg = cfg
 
+    def deep_loss(self, g: Grid, pw: PhysWeights, t: float, dt: float):
+        """(L_sigma, L_u) of the deep network set by set_weights_deep, in one call (fields stay in context scratch)."""
+        ls, lu = C.c_float(), C.c_float()
+        cg, cw = g.c(), pw.c()
+        check(self._lib.physad_deep_loss_host(self._h, C.byref(cg), C.byref(cw), C.c_float(t), C.c_float(dt), C.byref(ls),
+                                              C.byref(lu)), "deep_loss")
+        return np.float32(ls.value), np.float32(lu.value)
+
     def set_deep_mode(self, mode: int) -> None:
         """0: strict fp32 (bit-exact, default); 1: hidden layers on the tensor cores with three-term bf16 operands (~1e-6)."""
         check(self._lib.physad_set_deep_mode(self._h, C.c_int(mode)), "set_deep_mode")

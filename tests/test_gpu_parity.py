@@ -240,6 +240,27 @@ def test_deep_fast_mode_tracks_the_strict_kernel(ctx, port, H, L, shape):
     assert np.array_equal(ctx.mlp_grid_infer_deep(g, 0.3).cpu().numpy(), strict)   # back to the parity mode
 
 
+def test_deep_loss_one_call_equals_the_stagewise_calls(ctx, port):
+    """physad_deep_loss_host = generate_fields_deep + phys_loss on context scratch: same losses as the two calls, in both
+    arithmetic modes."""
+    rng = np.random.default_rng(3)
+    og = OGrid(48, 20, 7, 1, 1, 1, 2e-3, True)
+    g = _g(og)
+    H, L = 64, 3
+    W1, b1, W2, b2 = port.mlp_random_init(H, 9, 0.25)
+    Wh = rng.uniform(-0.2, 0.2, (L - 1) * H * H).astype(np.float32)
+    bh = rng.uniform(-0.2, 0.2, (L - 1) * H).astype(np.float32)
+    ctx.set_weights_deep(_cfg(H), L, W1, b1, Wh, bh, W2, b2)
+    for mode in (0, 1):
+        ctx.set_deep_mode(mode)
+        try:
+            want = ctx.phys_loss(g, _pw(1.3, 0.7), ctx.mlp_generate_fields_deep(g, 0.25, 2e-3))
+            got = ctx.deep_loss(g, _pw(1.3, 0.7), 0.25, 2e-3)
+            assert got[0] == want[0] and got[1] == want[1]
+        finally:
+            ctx.set_deep_mode(0)
+
+
 def test_deep_fast_mode_one_hidden_layer_and_bad_mode(ctx, port):
     """With one hidden layer there is no hidden -> hidden contraction: the default route is the reference-pinned kernel in
     either mode (bit-identical), the forced deep kernel refuses mode 1 with PHYSAD_E_UNSUPPORTED -- never a silent switch

@@ -75,6 +75,15 @@ def test_wide_mlp_through_the_reference_names():
     assert "[PASS]" in r.stdout and "[FAIL]" not in r.stdout
 
 
+def test_deep_mlp_through_the_cxx_api():
+    """tests/refprogs/deep_mlp_dropin.cpp (ours): phys::mlp_phys_loss_deep_cuda with one hidden layer against the reference's
+    CPU path (1e-6), with three hidden layers against the reference's layer rule applied again on the CPU + the reference's
+    cpu_phys_loss_forward -- strict mode 1e-6, tensor-core mode 1e-4."""
+    r = _run("deep_mlp_dropin")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("[PASS]") == 3 and "[FAIL]" not in r.stdout
+
+
 def test_closed_loop_program_through_the_cxx_api():
     """tests/refprogs/closed_loop_train.cpp (ours, in the reference's style): Adam over phys::mlp_phys_loss_grad_cuda;
     the plan's acceptance criterion (REQUIREMENT.md:164-169): L falls >= 90 % within K steps."""
