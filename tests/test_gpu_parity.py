@@ -240,6 +240,32 @@ def test_deep_fast_mode_tracks_the_strict_kernel(ctx, port, H, L, shape):
     assert np.array_equal(ctx.mlp_grid_infer_deep(g, 0.3).cpu().numpy(), strict)   # back to the parity mode
 
 
+@pytest.mark.parametrize("H,L", [(128, 3), (128, 5), (64, 5), (32, 2)])
+def test_deep_fast_mode_repeatability_stress(ctx, port, H, L):
+    """The tensor-core kernel hands tensor-memory operands between an MMA warp and two epilogue groups through mbarriers
+    (resident and streamed weights).  A missing ordering edge would show up as run-to-run differences: 25 launches over a
+    grid with many row tiles per block must be bit-identical, fields and infer alike."""
+    rng = np.random.default_rng(H + L)
+    og = OGrid(256, 96, 12, 1, 1, 1, 2e-3, True)
+    g = _g(og)
+    W1, b1, W2, b2 = port.mlp_random_init(H, 11, 0.25)
+    Wh = rng.uniform(-0.2, 0.2, (L - 1) * H * H).astype(np.float32)
+    bh = rng.uniform(-0.2, 0.2, (L - 1) * H).astype(np.float32)
+    ctx.set_weights_deep(_cfg(H), L, W1, b1, Wh, bh, W2, b2)
+    ctx.set_deep_mode(1)
+    try:
+        import torch
+        ref = [x.clone() for x in ctx.mlp_generate_fields_deep(g, 0.25, 2e-3)]
+        ref_i = ctx.mlp_grid_infer_deep(g, 0.25).clone()
+        for _ in range(25):
+            f = ctx.mlp_generate_fields_deep(g, 0.25, 2e-3)
+            assert all(torch.equal(x, y) for x, y in zip(ref, f))
+            assert torch.equal(ctx.mlp_grid_infer_deep(g, 0.25), ref_i)
+        assert torch.isfinite(ref_i).all()
+    finally:
+        ctx.set_deep_mode(0)
+
+
 def test_deep_loss_one_call_equals_the_stagewise_calls(ctx, port):
     """physad_deep_loss_host = generate_fields_deep + phys_loss on context scratch: same losses as the two calls, in both
     arithmetic modes."""
