@@ -71,6 +71,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int H, bool FIELDS>
+// 17 warps: one scheduler hosts five of them, so 16384 / (5 x 32) = 102 -> 96 registers per thread is the most that can
+// launch (a __maxnreg__(112) build failed with "too many resources"); the <128, fields> variant spills 24 bytes at that cap.
 __global__ void __launch_bounds__(TcThreads<H>::value, 1)
     k_mlp_deep_tc(const __grid_constant__ MlpConst<H> w, const __grid_constant__ DeepArgs a, const uint8_t* __restrict__ wparts,
                   const int nbuf, unsigned long long* __restrict__ prof) {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
                 }
                 __syncwarp();
             };
-            uint32_t ph_w[2] = {0, 0};
+            uint32_t ph_w = 0;        // phase bits of bar_wbuf[0], bar_wbuf[1]
             if (resident) {
                 mbar_wait(bar_w, 0);
             } else {
@@ -181,8 +183,8 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
                     const uint32_t a_in = tbase + A_COL + uint32_t(step & 1) * A_BUF;
                     const uint32_t wl = w0 + uint32_t(resident ? l : int(step & 1)) * 3 * TERM_BYTES;
                     if (!resident) {
-                        mbar_wait(&bar_wbuf[step & 1], ph_w[step & 1]);
-                        ph_w[step & 1] ^= 1;
+                        mbar_wait(&bar_wbuf[step & 1], (ph_w >> (step & 1)) & 1u);
+                        ph_w ^= 1u << (step & 1);
                     }
                     const uint32_t b_lo = (wl >> 4) | ((LBO >> 4) << 16), b_hi = (SBO >> 4) | (1u << 14);   // smem_desc(), in two words
 #pragma unroll
