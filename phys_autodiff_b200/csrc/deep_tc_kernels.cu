@@ -402,9 +402,262 @@ __global__ void __launch_bounds__(TcThreads<H>::value, 1)
     if (warp == MMA_WARP) tmem_free<TmemCols<H>::value>(tbase);
 }
 
+// ---- H <= 64: TWO row tiles in flight ------------------------------------------------------------------------------------
+// At H <= 64 a tile needs only H + 3 H/2 <= 160 tensor-memory columns and the kernel above is bound by its CUDA-core
+// epilogue (the split and drain work is O(H) per row and layer, the MMA work O(H^2)), whose threads wait a quarter of the time
+// for "their" MMAs.  Here two row tiles ("slots") alternate instead: while the tensor pipe runs slot 0's layer, slot 1's
+// eight epilogue warps drain, split and refill slot 1's A operand, and vice versa -- so a layer is plain full-width MMAs
+// (N = H, no N/K halves, ONE A operand per slot: its epilogue and its MMAs never overlap), 24 instead of 48 per layer.
+// Used when every layer image is resident in shared memory; the streamed case keeps the kernel above.
+constexpr int TC2_THREADS = (16 + 1) * 32;       // 2 slots x 4 lane quarters x 2 column halves + the MMA warp
+
+template <int H>
+size_t smem_for2(int nl) {
+    return size_t(nl) * 3 * H * H * 2 + 28 * H + 16 * H + size_t(nl) * H * 4 + 2 * 2 * TILE * 16 + 96;
+}
+
+template <int H, bool FIELDS>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+    k_mlp_deep_tc2(const __grid_constant__ MlpConst<H> w, const __grid_constant__ DeepArgs a, const uint8_t* __restrict__ wparts) {
+    static_assert(H == 32 || H == 64, "two tiles of H + 3 H/2 columns each");
+    constexpr int NS = FIELDS ? 3 : 1;
+    constexpr int HH = H / 2;                    // hidden units / accumulator columns per epilogue thread; columns of one A term
+    constexpr uint32_t SLOT_COLS = H + 3 * HH;   // D | A term 1 | term 2 | term 3
+    constexpr uint32_t TMEM_COLS = H == 64 ? 512u : 256u;
+    constexpr uint32_t LBO = 16 * H, SBO = 128;
+    constexpr uint32_t TERM_BYTES = H * H * 2;
+    constexpr int NCH = HH / 16;
+    constexpr int MMA_WARP = 16;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int nl = a.hidden_layers - 1;
+    const size_t w_bytes = size_t(nl) * 3 * TERM_BYTES;
+    // layer-1 pairs [7][H/2]: 0..2 W1[., 0..2] half-swapped | 3 b1 | 4..6 fl(W1[., 3] t_s) for the three slices
+    float2* s_l1 = reinterpret_cast<float2*>(smem + w_bytes);
+    float4* s_w2 = reinterpret_cast<float4*>(smem + w_bytes + 28 * H);             // {W2[0..3, h]}
+    float* s_bh = reinterpret_cast<float*>(smem + w_bytes + 44 * H);               // [nl][H]
+    float4* s_part = reinterpret_cast<float4*>(smem + w_bytes + 44 * H + size_t(nl) * H * 4);   // [slot][2][TILE] lower half's outputs
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 2 * TILE);
+    uint64_t* bar_w = bars;                      // layer images landed
+    uint64_t* bar_full = bars + 1;               // [slot] the slot's layer is complete (tcgen05.commit)
+    uint64_t* bar_ready = bars + 3;              // [slot] the slot's A operand is written and its D drained (256 arrivals)
+    uint64_t* bar_part = bars + 5;               // [slot] the lower column half's partial outputs are in s_part (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+    const int tid = threadIdx.x, warp = tid >> 5, m = tid & (TILE - 1);
+    const int slot = tid >> 8, half = (tid >> 7) & 1;
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        for (int s_ = 0; s_ < 2; ++s_) {
+            mbar_init(&bar_full[s_], 1);
+            mbar_init(&bar_ready[s_], 2 * TILE);
+            mbar_init(&bar_part[s_], TILE);
+        }
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc<TMEM_COLS>(tmem_slot);
+    for (int q = tid; q < H / 2; q += TC2_THREADS) {
+        const float4 ra = __ldg(reinterpret_cast<const float4*>(a.W1) + 2 * q), rb = __ldg(reinterpret_cast<const float4*>(a.W1) + 2 * q + 1);
+        s_l1[q] = make_float2(rb.x, ra.x);                // half-swapped for mul2_rn / add2_rn_swapped (mlp_eval.cuh)
+        s_l1[H / 2 + q] = make_float2(rb.y, ra.y);
+        s_l1[2 * (H / 2) + q] = make_float2(rb.z, ra.z);
+        s_l1[3 * (H / 2) + q] = make_float2(__ldg(a.b1 + 2 * q), __ldg(a.b1 + 2 * q + 1));
+#pragma unroll
+        for (int sl = 0; sl < 3; ++sl)                    // fl(W1[.,3] t_s): the product the strict path rounds once per slice
+            s_l1[(4 + sl) * (H / 2) + q] = make_float2(__fmul_rn(ra.w, a.tc[sl]), __fmul_rn(rb.w, a.tc[sl]));
+    }
+    for (int h = tid; h < H; h += TC2_THREADS) {
+        const float4 v = w.w2[h];                          // {W2[1,h], W2[0,h], W2[3,h], W2[2,h]}
+        s_w2[h] = make_float4(v.y, v.x, v.w, v.z);
+    }
+    for (int i = tid; i < nl * H; i += TC2_THREADS) s_bh[i] = __ldg(a.bh + i);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, uint32_t(w_bytes));
+        for (int i = 0; i < nl * 3; ++i) bulk_g2s(smem + size_t(i) * TERM_BYTES, wparts + size_t(i) * TERM_BYTES, TERM_BYTES, bar_w);
+    }
+
+    const uint32_t tbase = *tmem_slot;
+    const long long n_slab = (long long)(a.z_end - a.z_begin) * a.ny * a.nx;
+    const long long tiles = (n_slab + TILE - 1) / TILE;
+    const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long my_rts = my_tiles * NS;      // row tiles of this block in order (tile, slice); slot s takes s, s + 2, ...
+
+    if (warp == MMA_WARP) {
+        mbar_wait(bar_w, 0);
+        const uint32_t idesc = idesc_bf16_f32(TILE, H);
+        const uint32_t w0 = smem_u32(smem);
+        const uint32_t b_hi = (SBO >> 4) | (1u << 14);
+        const int PA[6] = {2, 1, 0, 1, 0, 0}, PB[6] = {0, 1, 2, 0, 1, 0};   // t3 t1, t2 t2, t1 t3, t2 t1, t1 t2, t1 t1
+        uint32_t ph_ready = 0;                   // phase bits of bar_ready[0], [1]
+        for (long long rt0 = 0; rt0 < my_rts; rt0 += 2) {
+#pragma unroll 1
+            for (int l = 0; l < nl; ++l) {
+                const uint32_t b_lo = ((w0 + uint32_t(l) * 3 * TERM_BYTES) >> 4) | ((LBO >> 4) << 16);
+#pragma unroll
+                for (int s_ = 0; s_ < 2; ++s_) {
+                    if (rt0 + s_ < my_rts) {
+                        mbar_wait(&bar_ready[s_], (ph_ready >> s_) & 1u);
+                        ph_ready ^= 1u << s_;
+                        fence_after_sync();
+                        const uint32_t d_t = tbase + uint32_t(s_) * SLOT_COLS, a_t = d_t + H;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ps = 0; ps < 6; ++ps) {
+#pragma unroll
+                                for (int ks = 0; ks < H / 16; ++ks)
+                                    mma_bf16_ts(d_t, a_t + PA[ps] * HH + ks * 8, b_lo + ((PB[ps] * TERM_BYTES + uint32_t(ks) * 2 * LBO) >> 4), b_hi,
+                                                idesc, !(ps == 0 && ks == 0));
+                            }
+                            mma_commit(&bar_full[s_]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const uint32_t lane_t = tbase + (uint32_t((warp & 3) * 32) << 16) + uint32_t(slot) * SLOT_COLS;   // this slot's D, row m
+        const uint32_t a_t = lane_t + H;
+        const int plane = a.nx * a.ny;
+        const size_t n = size_t(n_slab);
+        const float4 b2 = w.b2;
+        float4* part = s_part + slot * 2 * TILE;
+        uint32_t ph_full = 0, ph_part = 0;
+        long long k_rt = 0;                      // how many row tiles this slot has finished (parity picks the s_part buffer)
+        for (long long rt = slot; rt < my_rts; rt += 2, ++k_rt) {
+            const long long tile = blockIdx.x + (rt / NS) * gridDim.x;
+            const int sl = int(rt % NS);
+            const long long i_pt = tile * TILE + m;
+            // ---- layer 1 (strict fp32, the arithmetic of mlp_eval.cuh): this thread's H/2 hidden units of row m -> A -------------
+            {
+                const long long p = i_pt < n_slab ? i_pt : n_slab - 1;   // tail tile: evaluate a valid point, never stored
+                const int zl = int(p / plane), rem = int(p - (long long)zl * plane);
+                const int y = rem / a.nx, x = rem - y * a.nx;
+                const f32x2 cx2 = bcast2(__ldg(a.cxs + x)), cy2 = bcast2(__ldg(a.cys + y)), cz2 = bcast2(__ldg(a.czs + a.z_begin + zl));
+                const float2* bt = s_l1 + (4 + (FIELDS ? sl : 1)) * (H / 2);
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    uint32_t t1[8], t2[8], t3[8];
+                    const int q0 = (half * HH + c * 16) / 2;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int q = q0 + j;
+                        f32x2 z2 = add2_rn_swapped(pack2(s_l1[3 * (H / 2) + q]), mul2_rn(pack2(s_l1[q]), cx2));
+                        z2 = add2_rn_swapped(z2, mul2_rn(pack2(s_l1[H / 2 + q]), cy2));
+                        z2 = add2_rn_swapped(z2, mul2_rn(pack2(s_l1[2 * (H / 2) + q]), cz2));
+                        z2 = add2_rn(z2, pack2(bt[q]));
+                        split3_relu(z2, t1[j], t2[j], t3[j]);
+                    }
+                    tmem_st8(a_t + uint32_t(q0), t1);
+                    tmem_st8(a_t + HH + uint32_t(q0), t2);
+                    tmem_st8(a_t + 2 * HH + uint32_t(q0), t3);
+                }
+                tmem_st_wait();
+                fence_before_sync();
+                mbar_arrive(&bar_ready[slot]);
+            }
+            f32x2 y01 = pack2(0.f, 0.f), y23 = pack2(0.f, 0.f);
+#pragma unroll 1
+            for (int l = 0; l < nl; ++l) {
+                const bool last = l == nl - 1;
+                mbar_wait(&bar_full[slot], ph_full);
+                ph_full ^= 1;
+                __syncwarp();             // tcgen05.ld / .st are warp-collective
+                fence_after_sync();
+                uint32_t r[NCH][16];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tmem_ld16(lane_t + uint32_t(half * HH + c * 16), r[c]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int g0 = half * HH + c * 16;
+                    const float4* bp = reinterpret_cast<const float4*>(s_bh + l * H + g0);
+                    f32x2 v2[8];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 b = bp[j4];
+                        v2[2 * j4] = add2_rn(pack2(__uint_as_float(r[c][4 * j4]), __uint_as_float(r[c][4 * j4 + 1])), pack2(b.x, b.y));
+                        v2[2 * j4 + 1] = add2_rn(pack2(__uint_as_float(r[c][4 * j4 + 2]), __uint_as_float(r[c][4 * j4 + 3])), pack2(b.z, b.w));
+                    }
+                    if (!last) {
+                        // the slot's MMAs have completed (full), so its ONE A operand can be overwritten in place
+                        uint32_t t1[8], t2[8], t3[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) split3_relu(v2[j], t1[j], t2[j], t3[j]);
+                        tmem_st8(a_t + uint32_t(g0 / 2), t1);
+                        tmem_st8(a_t + HH + uint32_t(g0 / 2), t2);
+                        tmem_st8(a_t + 2 * HH + uint32_t(g0 / 2), t3);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float va, vb;
+                            unpack2(v2[j], va, vb);
+                            const float4 oa = s_w2[g0 + 2 * j], ob = s_w2[g0 + 2 * j + 1];
+                            const f32x2 aa = bcast2(relu_ref(va)), ab = bcast2(relu_ref(vb));
+                            y01 = fma2(pack2(oa.x, oa.y), aa, y01);
+                            y23 = fma2(pack2(oa.z, oa.w), aa, y23);
+                            y01 = fma2(pack2(ob.x, ob.y), ab, y01);
+                            y23 = fma2(pack2(ob.z, ob.w), ab, y23);
+                        }
+                    }
+                }
+                if (!last) {
+                    tmem_st_wait();
+                    fence_before_sync();
+                    mbar_arrive(&bar_ready[slot]);
+                }
+            }
+            // ---- outputs: the lower column half hands its partial sums to the upper one, which stores --------------------------------
+            float y0, y1, y2, y3;
+            unpack2(y01, y0, y1);
+            unpack2(y23, y2, y3);
+            float4* pbuf = part + (k_rt & 1) * TILE;
+            if (half == 0) {
+                pbuf[m] = make_float4(y0, y1, y2, y3);
+                mbar_arrive(&bar_part[slot]);
+            } else {
+                // waited for BEFORE this thread's next arrival on ready (the next row tile's layer 1): the lower half cannot be
+                // two row tiles ahead, so the barrier is never two phases ahead and the two s_part buffers suffice
+                mbar_wait(&bar_part[slot], ph_part);
+                ph_part ^= 1;
+                if (i_pt < n_slab) {
+                    const float4 o = pbuf[m];
+                    y0 = (b2.x + o.x) + y0; y1 = (b2.y + o.y) + y1; y2 = (b2.z + o.z) + y2; y3 = (b2.w + o.w) + y3;
+                    if (FIELDS) {
+                        a.sigma[sl][i_pt] = y0;
+                        a.u[sl][i_pt] = y1;
+                        a.u[sl][n + i_pt] = y2;
+                        a.u[sl][2 * n + i_pt] = y3;
+                    } else {
+                        a.out_aos[i_pt] = make_float4(y0, y1, y2, y3);
+                    }
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_free<TMEM_COLS>(tbase);
+}
+
 template <int H, bool FIELDS>
 int launch_t(const void* mlp_const, const DeepArgs& a, const uint8_t* wparts, int grid_blocks, cudaStream_t st) {
     const int nl = a.hidden_layers - 1, nbuf = weight_buffers<H>(nl);
+    if constexpr (H <= 64) {
+        // every layer image resident: two row tiles in flight (k_mlp_deep_tc2); PHYSAD_DEEP_TC_ONE_TILE keeps the kernel above
+        static const bool one_tile = getenv("PHYSAD_DEEP_TC_ONE_TILE") != nullptr;
+        size_t smem2 = smem_for2<H>(nl);
+        if (!one_tile && smem2 <= SMEM_CAP) {
+            if (smem2 < MIN_SMEM) smem2 = MIN_SMEM;
+            cudaError_t e2 = cudaFuncSetAttribute(k_mlp_deep_tc2<H, FIELDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2));
+            if (e2 != cudaSuccess) return int(e2);
+            k_mlp_deep_tc2<H, FIELDS><<<grid_blocks, TC2_THREADS, smem2, st>>>(*static_cast<const MlpConst<H>*>(mlp_const), a, wparts);
+            return int(cudaGetLastError());
+        }
+    }
     size_t smem = smem_for<H>(nl, nbuf);
     if (smem < MIN_SMEM) smem = MIN_SMEM;
     cudaError_t e = cudaFuncSetAttribute(k_mlp_deep_tc<H, FIELDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
