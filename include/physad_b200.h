@@ -138,7 +138,8 @@ int physad_set_weights_deep(physad_ctx* ctx, const physad_mlp_config* cfg, int h
  *      FFMA-contracted evaluation such as the reference's own CUDA kernels (src/mlp_cuda.cu).  Needs hidden_layers >= 2
  *      (with one hidden layer there is no hidden -> hidden contraction: PHYSAD_E_UNSUPPORTED from the forced deep kernel;
  *      the default route for one hidden layer is the reference-pinned kernel in either mode).  Layer images stay resident
- *      in shared memory when they fit (H = 128: <= 3 hidden layers), else they are streamed from L2.  Layer 1 stays strict. */
+ *      in shared memory when they fit (H = 128: <= 3 hidden layers), else they are streamed from L2; at H <= 64 two row
+ *      tiles are in flight per SM.  Layer 1 stays strict. */
 int physad_set_deep_mode(physad_ctx* ctx, int mode);
 /* Stage-wise evaluation over the grid (coordinates from the index); outputs as the one-layer calls above. */
 int physad_mlp_grid_infer_deep_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float* out,
