@@ -1,25 +1,33 @@
 // Deeper coordinate MLPs, fast mode: hidden -> hidden layers on tcgen05 with three-term bf16 operands.
 // What is computed, and why it is additive / not bit-exact: deep_tc_kernels.cuh.
 //
-// One 288-thread block per SM, persistent over "row tiles" = 128 points x one time slice (row = (point, slice), 128 rows =
-// the M of an MMA).  Warp-specialised, ONE row tile in flight, pipelined across the two halves of the hidden width:
-//   * warps 0-3 ("group 0") and 4-7 ("group 1"): thread m of a group owns row m = tensor-memory lane m (a warp may only
-//     touch lanes 32 (w % 4) ..); group g produces hidden units [g H/2, (g+1) H/2) in layer 1 and drains accumulator
-//     columns of the same range after every layer;  warp 8: lane 0 issues every MMA, the warp owns the tensor memory;
+// Two kernels, one persistent block per SM over "row tiles" = 128 points x one time slice (row = (point, slice), 128 rows =
+// the M of an MMA):
+//
+// k_mlp_deep_tc (H = 128, and any shape whose layer images must be streamed): ONE row tile in flight, pipelined across the
+// two halves of the hidden width.  WPG = 2 epilogue warps per (group, lane quarter) for H >= 64 (544 threads), 1 for H = 32.
+//   * epilogue group g (warps [4 WPG g, 4 WPG (g+1))): thread m owns row m = tensor-memory lane m (a warp may only touch
+//     lanes 32 (w % 4) ..); the group produces hidden units [g H/2, (g+1) H/2) in layer 1 and drains the accumulator
+//     columns of the same range after every layer, each thread H / (2 WPG) of them;  the last warp: one elected lane issues
+//     every MMA (and the weight streaming), the warp owns the tensor memory;
 //   * tensor memory columns: [0, H) the fp32 accumulators D (halves D0 | D1), then TWO A operands (activations) of
 //     3 bf16 terms x H/2 columns each (two K elements per 32-bit column), written by tcgen05.st from the thread that
 //     owns the row: activations never visit shared memory.  Layer t reads A[t & 1], its epilogue writes A[(t+1) & 1];
-//   * shared memory: the operand images of ALL hidden -> hidden layers (3 terms x H x H bf16 each, K-major no-swizzle
-//     core matrices, written by deep_tc_pack_layer on the host and bulk-copied once per block), layer-1 pairs, output
-//     layer, biases;
+//   * shared memory: the operand images of the hidden -> hidden layers (3 terms x H x H bf16 each, K-major no-swizzle
+//     core matrices, written by deep_tc_pack_layer on the host and bulk-copied; all resident when they fit, else two
+//     buffers refilled one layer ahead), layer-1 pairs, output layer, biases;
 //   * a layer = four blocks (N half n, K half k) of 6 term pairs x H/32 K slices, issued n0k0 n0k1 | commit full[0] |
 //     n1k0 n1k1 | commit full[1].  Block (n, k) of the NEXT layer needs only "group k has written its K half of the
-//     other A operand and group n has drained D_n" = mbarrier ready[k] / ready[n] (128 arrivals each), so group 0's
-//     epilogue runs under this layer's n1 blocks and group 1's under the next layer's n0k0 block: the tensor pipe only
-//     waits when an epilogue takes longer than a quarter of a layer;
-//   * after the last hidden layer a group accumulates its share of the four outputs (fp32 FMA) instead of splitting;
+//     other A operand and group n has drained D_n" = mbarrier ready[k] / ready[n], so group 0's epilogue runs under this
+//     layer's n1 blocks and group 1's under the next layer's n0k0 block: the tensor pipe only waits when an epilogue
+//     takes longer than a quarter of a layer;
+//   * after the last hidden layer a thread accumulates its share of the four outputs (fp32 FMA) instead of splitting;
 //     the next row tile's layer 1 is computed BEFORE waiting for that last layer (its A operand is free), so it is off
-//     the critical path as well.  Group 0 hands its partial outputs to group 1 through shared memory; group 1 stores.
+//     the critical path as well.  The last column share of a row collects the others' partial outputs through shared
+//     memory and stores.
+//
+// k_mlp_deep_tc2 (H <= 64, every layer image resident): TWO row tiles in flight, see the comment above it.
+//
 // Governing roofline: the bf16 tensor pipe at 6 MMA passes per fp32-equivalent contraction: 2 H^2 x 6 flop per row and
 // layer against MEASURED_PEAKS' dense bf16 figure.
 #include "deep_tc_kernels.cuh"
