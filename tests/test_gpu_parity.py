@@ -240,6 +240,25 @@ def test_deep_fast_mode_tracks_the_strict_kernel(ctx, port, H, L, shape):
     assert np.array_equal(ctx.mlp_grid_infer_deep(g, 0.3).cpu().numpy(), strict)   # back to the parity mode
 
 
+def test_tcgen05_layout_probe():
+    """tools/tc_probe.cu: D = A B^T on exact small integers through the same descriptor / packing helpers the tensor-core
+    kernels use (A in tensor memory or in shared memory, B in the K-major no-swizzle core-matrix layout).  The conventions the
+    kernels rely on must give zero mismatches; the deliberately wrong variants (LBO/SBO exchanged, K pair order swapped) must not."""
+    import os, re, subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "_bin", "tc_probe")
+    if not os.path.exists(exe):
+        pytest.skip("tools/_bin/tc_probe not built (python __graft_entry__.py builds it)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = re.findall(r"N=(\d+) K=(\d+) tmemA=(\d) swapLS=(\d) swapPack=(\d): (\d+) / (\d+) mismatches", r.stdout)
+    assert len(rows) == 11, r.stdout
+    for N, K, tm, sl, sp, bad, tot in rows:
+        if sl == "0" and sp == "0":
+            assert bad == "0", r.stdout
+        else:
+            assert int(bad) > int(tot) // 2, r.stdout
+
+
 @pytest.mark.parametrize("H,L", [(128, 3), (128, 5), (64, 5), (32, 2)])
 def test_deep_fast_mode_repeatability_stress(ctx, port, H, L):
     """The tensor-core kernel hands tensor-memory operands between an MMA warp and two epilogue groups through mbarriers
