@@ -141,6 +141,13 @@ int physad_set_weights_deep(physad_ctx* ctx, const physad_mlp_config* cfg, int h
  *      in shared memory when they fit (H = 128: <= 3 hidden layers), else they are streamed from L2; at H <= 64 two row
  *      tiles are in flight per SM.  Layer 1 stays strict. */
 int physad_set_deep_mode(physad_ctx* ctx, int mode);
+/* The operand image mode 1 keeps of ONE hidden -> hidden layer (host function, no GPU needed; physad_set_weights_deep calls
+ * it): W = [H out][H in] row-major -> three bf16 terms t1 + t2 + t3 = W (each the round-to-nearest bf16 of what the previous
+ * ones left), term p at element offset p*H*H, element (g, h) of a term at (h/8)*(H/8)*64 + (g/8)*64 + (g%8)*8 + (h%8): the
+ * "K-major, no swizzle" core-matrix layout of a tcgen05 shared-memory descriptor with SBO = 128 B, LBO = 16*H B.
+ * physad_deep_tc_layer_bytes(H) = 3*H*H*2 (0 for widths that are not built). */
+size_t physad_deep_tc_layer_bytes(int H);
+int physad_deep_tc_pack_layer(int H, const float* W, unsigned char* image);
 /* Stage-wise evaluation over the grid (coordinates from the index); outputs as the one-layer calls above. */
 int physad_mlp_grid_infer_deep_dev(physad_ctx* ctx, const physad_grid* g, const physad_slab* slab, float t, float* out,
                                    void* stream);

@@ -83,7 +83,7 @@ EXPORTS = [
     "physad_ctx_create", "physad_ctx_destroy", "physad_ctx_sm_count", "physad_set_weights",
     "physad_mlp_forward_dev", "physad_mlp_forward_host", "physad_mlp_backward_dev", "physad_mlp_backward_host",
     "physad_mlp_grid_infer_dev", "physad_mlp_grid_infer_host",
-    "physad_set_weights_deep", "physad_set_deep_mode", "physad_mlp_grid_infer_deep_dev", "physad_mlp_generate_fields_deep_dev", "physad_deep_loss_host",
+    "physad_set_weights_deep", "physad_set_deep_mode", "physad_deep_tc_layer_bytes", "physad_deep_tc_pack_layer", "physad_mlp_grid_infer_deep_dev", "physad_mlp_generate_fields_deep_dev", "physad_deep_loss_host",
     "physad_mlp_generate_fields_dev", "physad_mlp_generate_fields_host",
     "physad_phys_residuals_dev", "physad_phys_residuals_host",
     "physad_phys_loss_dev", "physad_phys_loss_host", "physad_phys_loss_slab_dev",
@@ -124,6 +124,7 @@ def lib() -> C.CDLL:
         _LIB.physad_error_string.restype = C.c_char_p
         _LIB.physad_launch_count.restype = C.c_uint64
         _LIB.physad_finalize_loss.restype = None
+        _LIB.physad_deep_tc_layer_bytes.restype = C.c_size_t
     return _LIB
 
 

@@ -988,6 +988,15 @@ int physad_set_weights_deep(physad_ctx* c, const physad_mlp_config* cfg, int hid
     return 0;
 }
 
+size_t physad_deep_tc_layer_bytes(int H) { return (H == 32 || H == 64 || H == 128) ? deep_tc_layer_bytes(H) : 0; }
+
+int physad_deep_tc_pack_layer(int H, const float* W, unsigned char* image) {
+    if (!W || !image) return fail(PHYSAD_E_INVALID, "deep_tc_pack_layer: null argument");
+    if (H != 32 && H != 64 && H != 128) return fail(PHYSAD_E_UNSUPPORTED, "deep_tc_pack_layer: H in {32, 64, 128}");
+    deep_tc_pack_layer(H, W, image);
+    return 0;
+}
+
 int physad_set_deep_mode(physad_ctx* c, int mode) {
     if (!c) return fail(PHYSAD_E_INVALID, "set_deep_mode: null context");
     if (mode != 0 && mode != 1) return fail(PHYSAD_E_INVALID, "set_deep_mode: 0 (strict fp32) or 1 (tensor cores, three-term bf16)");

@@ -174,3 +174,26 @@ def test_fused_work_partition_properties(libpath):
             costs.append((b - a) + 0.9 * segs)
         ideal = (tiles * planes + 0.9 * max(tiles, n - 1)) / (n - 1)
         assert max(costs) <= ideal + 2.9, (tiles, planes, slots, max(costs), ideal)  # one plane + one extra segment of slack
+
+
+@pytest.mark.parametrize("H", [32, 64, 128])
+def test_tensor_core_layer_image_is_an_exact_three_term_split_in_the_documented_layout(libpath, H):
+    """physad_deep_tc_pack_layer (host code, no GPU): the three bf16 terms add up to the fp32 weight to 2^-24 and sit where
+    include/physad_b200.h says -- the layout the MMA's shared-memory descriptor (SBO 128 B, LBO 16 H B) walks."""
+    import numpy as np
+    lib = C.CDLL(libpath)
+    lib.physad_deep_tc_layer_bytes.restype = C.c_size_t
+    assert lib.physad_deep_tc_layer_bytes(H) == 3 * H * H * 2 and lib.physad_deep_tc_layer_bytes(48) == 0
+    rng = np.random.default_rng(H)
+    W = rng.uniform(-0.2, 0.2, (H, H)).astype(np.float32)
+    W[0, 0], W[1, 1], W[2, 2] = 0.0, 1.0, np.float32(-3.1415927)
+    img = np.zeros(3 * H * H, dtype=np.uint16)
+    assert lib.physad_deep_tc_pack_layer(H, W.ctypes.data_as(C.c_void_p), img.ctypes.data_as(C.c_void_p)) == 0
+    g, h = np.meshgrid(np.arange(H), np.arange(H), indexing="ij")
+    off = (h // 8) * (H // 8) * 64 + (g // 8) * 64 + (g % 8) * 8 + (h % 8)
+    assert sorted(off.ravel().tolist()) == list(range(H * H))                 # a permutation of the tile
+    terms = [(img[p * H * H + off].astype(np.uint32) << 16).view(np.float32).astype(np.float64) for p in range(3)]
+    total = terms[0] + terms[1] + terms[2]
+    assert np.all(np.abs(total - W.astype(np.float64)) <= 2.0 ** -24 * np.abs(W) + 1e-45)
+    assert np.all(np.abs(terms[1]) <= 2.0 ** -8 * np.abs(terms[0]) + 1e-45) and np.all(np.abs(terms[2]) <= 2.0 ** -16 * np.abs(terms[0]) + 1e-45)
+    assert lib.physad_deep_tc_pack_layer(48, W.ctypes.data_as(C.c_void_p), img.ctypes.data_as(C.c_void_p)) != 0
