@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 5: MLP width/depth sweep at 256^3 (strict fp32, stage-wise: three time slices -> six fields,
 then the physics loss on those fields).  H in {32, 64, 128}, hidden layers L in {1..5}; L = 1 also shows the fused
-kernel.  Reports ms, Gpts/s and the fraction of the measured strict FMUL+FADD peak for the ALGORITHMIC flops
+kernel, L >= 2 also the tensor-core mode.  Reports ms, Gpts/s and the fraction of the measured strict FMUL+FADD peak for the ALGORITHMIC flops
 3 * (2*4H + (L-1)*2H^2 + 2*4H) + 3*L*H (ReLU) per point.  Prints JSON."""
 import argparse, json, os, statistics, sys
 
@@ -55,6 +55,15 @@ def main():
             row = {"H": H, "hidden_layers": L, "ms_fields": ms_mlp, "ms_phys_loss": ms_phys,
                    "gpts_per_s_total": g.N / (ms_mlp + ms_phys) / 1e6, "flops_per_point_mlp": flops,
                    "mlp_tflops": flops * g.N / (ms_mlp * 1e-3) / 1e12, "mlp_frac_of_strict_fp32": flops * g.N / (ms_mlp * 1e-3) / 1e12 / strict}
+            if L >= 2:     # the tensor-core mode of the same network (tcgen05, three-term bf16 operands; not bit-exact)
+                ctx.set_deep_mode(1)
+                try:
+                    ms_fast = timeit(lambda: ctx.mlp_generate_fields_deep(g, 0.25, 2e-3))
+                    row["ms_fields_tensor_cores"] = ms_fast
+                    row["tensor_core_speedup"] = ms_mlp / ms_fast
+                    row["bf16_tflops_issued"] = 3 * (L - 1) * 6 * 2 * H * H * g.N / (ms_fast * 1e-3) / 1e12
+                finally:
+                    ctx.set_deep_mode(0)
             if L == 1:
                 ctx.set_weights(MLPConfig(4, H, 4, True), W1, b1, W2, b2)
                 row["ms_fused_kernel"] = timeit(lambda: ctx.fused_loss_acc(g, 0.25, 2e-3))
