@@ -117,7 +117,8 @@ def test_strict_kernels_have_no_contracted_fma_in_mlp(libpath):
         m = re.search(r"Function : (\S+)", line)
         if m:
             cur = m.group(1)
-            counts[cur] = {"FFMA": 0, "FMUL": 0, "FADD": 0, "FFMA2": 0, "FMUL2": 0, "FADD2": 0}
+            counts[cur] = {"FFMA": 0, "FMUL": 0, "FADD": 0, "FFMA2": 0, "FMUL2": 0, "FADD2": 0,
+                           "UTCHMMA": 0, "LDTM": 0, "STTM": 0, "UBLKCP": 0}
             continue
         m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
         if m and cur:
@@ -137,6 +138,10 @@ def test_strict_kernels_have_no_contracted_fma_in_mlp(libpath):
     tcs = {k: v for k, v in counts.items() if "k_mlp_deep_tc" in k}
     assert len(tcs) == 10 and all(v["FMUL2"] >= 3 and v["FADD2"] >= v["FMUL2"] and v["FFMA"] == 0 and v["FFMA2"] in (32, 64)
                                  for v in tcs.values()), tcs
+    # ... and they really are tcgen05 kernels: tensor-core MMAs with tensor-memory operands (UTCHMMA), tensor-memory loads and
+    # stores in the epilogue (LDTM / STTM), bulk copies of the weight images (UBLKCP); nothing else in the library uses them
+    assert all(v["UTCHMMA"] >= 24 and v["LDTM"] >= 1 and v["STTM"] >= 6 and v["UBLKCP"] >= 1 for v in tcs.values()), tcs
+    assert all(v["UTCHMMA"] == 0 and v["LDTM"] == 0 for k, v in counts.items() if "k_mlp_deep_tc" not in k)
     tang = {k: v for k, v in counts.items() if "k_tangent_loss" in k}
     assert len(tang) == 3 and all(v["FMUL2"] > 0 and v["FADD2"] > 0 for v in tang.values()), tang
     gradk = {k: v for k, v in counts.items() if "k_phys_grad" in k}
